@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- edges/sec of the RGCN hot path on a PPI-shaped batch (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: graph_num_layers = 3 x sparse_rgcn_layer
+(hidden 256, ReLU, sum aggregation, in-degree normalisation) on one synthetic PPI-shaped batch
+(V = 2,245 nodes, M = 120,245 messages, L = 3 edge types).  edges/sec = M / step time, the reference's
+own counter (models/sparse_graph_model.py:285,310: sum of E_l per batch, counted once per batch).
+
+  value        device-timed (CUDA events), inputs + plan resident in HBM, the 3 layers replayed as one CUDA graph,
+               L2 flushed (256 MiB write) between timed steps.
+  e2e          the same metric through the public Python API from pinned HOST buffers: H2D of features +
+               adjacency + in-degrees, plan build, 3 layers, D2H of the final node states -- every step.
+  roofline     algorithmic bytes of one RGCN layer (M*(4D+12) + V*8D + L*D*D*4) / measured layer
+               time, against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+  cpu_baseline the torch-CPU restatement of the reference op order (oracle/ref_torch.py) on this box's cores.
+Multi-GPU: weak scaling, every rank owns its own batch (graphs are independent units: no collective on the
+data path); value = edges of all ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HIDDEN = 256
+NUM_LAYERS = 3
+NUM_NODES = 2245
+NUM_LINKS = 59000
+METRIC = "edges/sec (device-timed) RGCN PPI hidden=256"
+WORKLOAD = ("RGCN synthetic PPI-shaped batch: V=2245 nodes, M=120245 messages (59000 links fwd+bkwd + self loops), "
+            "L=3 edge types, hidden=256, 3 layers, ReLU, sum aggregation with 1/(c+1e-7) normalisation")
+
+
+def algorithmic_bytes_per_layer(V, M, L, D):
+    """one gathered source row + (src,tgt) pair + in-degree scale per message, every node row
+    read once and written once, the L weight matrices."""
+    return M * (4 * D + 8 + 4) + V * 8 * D + L * D * D * 4
+
+
+def make_inputs(seed):
+    import numpy as np
+    from tf_gnn_samples_b200 import batching, weights as W
+    batch = batching.ppi_like_batch(num_graphs=1, num_nodes=NUM_NODES, num_links=NUM_LINKS, seed=seed)
+    h0 = np.tanh(np.random.default_rng(seed + 1).standard_normal((batch.num_nodes, HIDDEN))).astype(np.float32)
+    layer_weights = [W.rgcn_weights(len(batch.adjacency_lists), HIDDEN, HIDDEN, seed=2 + 10 * i) for i in range(NUM_LAYERS)]
+    return batch, h0, layer_weights
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path.  TF1 cannot run here, so this times the
+    op-for-op torch-CPU restatement (oracle/ref_torch.py, kind "port") with all host threads."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref_torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch, h0, layer_weights = make_inputs(seed=0)
+    h = torch.as_tensor(h0)
+    adj = [torch.as_tensor(a, dtype=torch.int64) for a in batch.adjacency_lists]
+    cnt = torch.as_tensor(batch.type_to_num_incoming_edges)
+    ws = [{"edge_weights": [torch.as_tensor(k) for k in w["edge_weights"]]} for w in layer_weights]
+    t0 = time.perf_counter()
+    ref_torch.rgcn_stack(h, adj, cnt, ws)
+    t_full = time.perf_counter() - t0
+    # bounded sample: a step is one full 3-layer forward unless K of them would take more than ~4 minutes,
+    # in which case a step is ONE of the three (equal-cost) layers and the rate is scaled by 1/3
+    layers_per_step = NUM_LAYERS if t_full * (args.steps + args.warmup) <= 240.0 else 1
+    step_ws = ws[:layers_per_step]
+    for _ in range(args.warmup):
+        ref_torch.rgcn_stack(h, adj, cnt, step_ws)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref_torch.rgcn_stack(h, adj, cnt, step_ws)
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    value = batch.num_edges / (dt / args.steps * NUM_LAYERS / layers_per_step)
+    sample = "%d steps, each %d of the 3 RGCN layers over the full batch (%d edges); rate = edges / 3-layer time" % (
+        args.steps, layers_per_step, batch.num_edges)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference arm = torch-CPU restatement of gnns/rgcn.py op order "
+                   "(TF1 not installable); rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(batch, h0, layer_weights, budget_s=12.0):
+    import torch
+    from oracle import ref_torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h = torch.as_tensor(h0)
+    adj = [torch.as_tensor(a, dtype=torch.int64) for a in batch.adjacency_lists]
+    cnt = torch.as_tensor(batch.type_to_num_incoming_edges)
+    ws = [{"edge_weights": [torch.as_tensor(k) for k in w["edge_weights"]]} for w in layer_weights]
+    ref_torch.rgcn_stack(h, adj, cnt, ws)
+    times = []
+    t_start = time.perf_counter()
+    while time.perf_counter() - t_start < budget_s and len(times) < 40:
+        t0 = time.perf_counter()
+        ref_torch.rgcn_stack(h, adj, cnt, ws)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": batch.num_edges / med, "unit": "edges/s", "cores": cores, "kind": "port",
+            "sample": "%d full 3-layer forwards over the same batch (median %.1f ms each), torch-CPU restatement of "
+                      "gnns/rgcn.py:84-114" % (len(times), med * 1e3)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import tf_gnn_samples_b200 as G
+    from tf_gnn_samples_b200 import weights as W
+    from tf_gnn_samples_b200.engine import launch_count
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the engine has no CPU path")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    batch, h0, layer_weights = make_inputs(seed=rank)        # weak scaling: every rank owns its own batch
+    V, M, L = batch.num_nodes, batch.num_edges, len(batch.adjacency_lists)
+    ws = [W.to_torch(w, dev) for w in layer_weights]
+
+    # ---------------- resident inputs ----------------
+    h_dev = torch.as_tensor(h0).to(dev)
+    cnt_dev = torch.as_tensor(batch.type_to_num_incoming_edges).to(dev)
+    plan = G.GraphPlan(batch.adjacency_lists, V, device=dev)
+
+    def forward(h):
+        cur = h
+        for w in ws:
+            cur = G.sparse_rgcn_layer(cur, plan, cnt_dev, HIDDEN, activation_function="ReLU",
+                                      message_aggregation_function="sum", weights=w)
+        return cur
+
+    out_eager = forward(h_dev)
+    torch.cuda.synchronize()
+    n0 = launch_count()
+    forward(h_dev)
+    kernels_per_step = launch_count() - n0
+    # capture the 3 layers once; replay per step (no tracing compiler: a plain CUDA graph of our own kernels)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            forward(h_dev)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out_graph = forward(h_dev)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out_graph, out_eager), "CUDA-graph replay differs from eager execution"
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def timed_steps(fn, steps, warmup):
+        for _ in range(warmup):
+            flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()                                     # cold L2 for every timed step (not timed)
+            starts[i].record()
+            fn()
+            ends[i].record()
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        per = [s.elapsed_time(e) for s, e in zip(starts, ends)]   # ms
+        return sum(per), per
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    total_ms, per_step = timed_steps(graph.replay, args.steps, args.warmup)
+    # roofline leg: one layer (transform GEMM + edge-stage segment kernel), same cold-L2 protocol
+    layer_total_ms, _ = timed_steps(lambda: G.sparse_rgcn_layer(h_dev, plan, cnt_dev, HIDDEN, activation_function="ReLU",
+                                                                 weights=ws[0]), args.steps, args.warmup)
+    warm_ms = None
+    if True:                                                  # warm-L2 companion number (reported, not the headline)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            graph.replay()
+        e.record()
+        torch.cuda.synchronize()
+        warm_ms = s.elapsed_time(e) / args.steps
+    clocks = sampler.stop() if sampler else None
+
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    edges_all = sum_over_ranks(float(M))
+    value = edges_all / (ms_per_step * 1e-3)
+    layer_ms = max_over_ranks(layer_total_ms) / args.steps
+
+    # ---------------- e2e: host buffers -> public API -> host ----------------
+    pin = lambda a: torch.as_tensor(a).pin_memory()
+    h_host = pin(h0)
+    adj_host = [pin(np.ascontiguousarray(a)) for a in batch.adjacency_lists]
+    cnt_host = pin(batch.type_to_num_incoming_edges)
+    out_host = torch.empty((V, HIDDEN), dtype=torch.float32).pin_memory()
+    h2d = h_host.numel() * 4 + sum(a.numel() * 4 for a in adj_host) + cnt_host.numel() * 4
+    d2h = out_host.numel() * 4
+
+    def e2e_step():
+        hd = h_host.to(dev, non_blocking=True)
+        ad = [a.to(dev, non_blocking=True) for a in adj_host]
+        cd = cnt_host.to(dev, non_blocking=True)
+        p = G.GraphPlan(ad, V, device=dev)
+        cur = hd
+        for w in ws:
+            cur = G.sparse_rgcn_layer(cur, p, cd, HIDDEN, activation_function="ReLU", weights=w)
+        out_host.copy_(cur, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()          # the caller needs the result
+        p.close()
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = edges_all / (e2e_s / args.steps)
+    assert np.allclose(out_host.numpy(), out_eager.cpu().numpy()), "e2e result differs from the resident run"
+
+    if rank != 0:
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    layer_bytes = algorithmic_bytes_per_layer(V, M, L, HIDDEN)
+    achieved = layer_bytes / (layer_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_layer")
+    line = {
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "flushed between timed steps (256 MiB write, untimed)",
+                   "step": "3 x sparse_rgcn_layer replayed as one CUDA graph (%d kernels)" % kernels_per_step,
+                   "parallelism": "independent batch per rank (graph-boundary sharding, no collective)",
+                   "warm_l2_ms_per_step": warm_ms, "per_layer_edges_per_s": M / (layer_ms * 1e-3)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "one RGCN layer = gemm_tf32x3 (node transform) + seg_reduce (edge stage)",
+                     "algorithmic_bytes_per_launch": layer_bytes, "ms_per_launch": layer_ms, "peak_source": peak_src,
+                     "note": "working set is L2-resident (compulsory traffic ~6 MB/layer): frac compares algorithmic bytes "
+                             "with HBM bandwidth, see DESIGN.md"},
+        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "what": "pinned host features+adjacency+in-degrees -> H2D -> GraphPlan build -> 3 layers -> D2H of final node states"},
+        "gpu_launches": int(kernels_per_step * args.steps),
+        "clocks": clocks,
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(batch, h0, layer_weights)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

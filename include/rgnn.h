@@ -1,0 +1,178 @@
+/*
+ * rgnn.h -- C ABI of the B200-native relational message-passing engine (librgnn.so).
+ *
+ * The reference (microsoft/tf-gnn-samples) has no FFI: its boundary is the Python call
+ * convention  Sparse_Graph_Model._apply_gnn_layer(node_representations, adjacency_lists,
+ * type_to_num_incoming_edges, num_timesteps)  (models/sparse_graph_model.py:204-225), served by
+ * gnns.sparse_<x>_layer(...) (gnns/__init__.py:1-7).  Each rgnn_<x>_forward below is what a
+ * ctypes binding of that layer function calls; the argument lists mirror the keyword
+ * arguments the model adapters pass (models/<x>_model.py), plus explicit weight pointers
+ * (the reference creates its weights inside the layer function under a tf.variable_scope).
+ *
+ * Conventions
+ *   return    0 = OK, negative = error (RGNN_E_*); message via rgnn_last_error() (thread-local).
+ *             Nothing throws across the ABI, nothing calls exit().
+ *   memory    every data pointer is a DEVICE pointer owned by the caller (16-byte aligned,
+ *             row-major fp32 / int32); "host array" arguments are small host-side tables
+ *             (pointer lists, sizes).  The library borrows pointers for the duration of the
+ *             call only.  Plans own their index buffers.
+ *   async     all work is enqueued on `stream` (a cudaStream_t passed as void*); forwards
+ *             make no hidden synchronisation and are CUDA-Graph capturable.  plan_create
+ *             synchronises the stream once (it sizes its buffers on the host).
+ *   threads   re-entrant on distinct plans/streams; one plan must not be used concurrently.
+ *   layouts   node states [V, D] fp32 row-major, D % 4 == 0; adjacency lists int32 [E_l, 2]
+ *             (col 0 = source, col 1 = target: gnns/rgcn.py:85-86); in-degrees fp32 [L, V]
+ *             (tasks/sparse_graph_task.py:145); weights in Keras orientation kernel[in, out]
+ *             (y = x . kernel) so reference checkpoints load without transposition.
+ */
+#ifndef RGNN_H_
+#define RGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RGNN_API __attribute__((visibility("default")))
+#else
+#define RGNN_API
+#endif
+
+#define RGNN_VERSION 100          /* 0.1.0 */
+#define RGNN_MAX_EDGE_TYPES 64
+#define RGNN_MAX_MLP_LAYERS 8
+#define RGNN_MAX_STATE_DIM 512    /* per-row register tile of the segment kernels */
+
+/* error codes */
+#define RGNN_OK 0
+#define RGNN_E_INVALID (-1)       /* bad argument (NULL, misaligned, dim % 4 != 0, unknown enum ...) */
+#define RGNN_E_CUDA (-2)          /* CUDA runtime error; message carries cudaGetErrorString */
+#define RGNN_E_WORKSPACE (-3)     /* workspace too small */
+#define RGNN_E_UNSUPPORTED (-4)   /* valid in the reference but outside this build's limits */
+
+/* utils/utils.py:36-58 get_activation (names lower-cased there) */
+enum rgnn_activation {
+  RGNN_ACT_LINEAR = 0, RGNN_ACT_TANH = 1, RGNN_ACT_RELU = 2, RGNN_ACT_LEAKY_RELU = 3,
+  RGNN_ACT_ELU = 4, RGNN_ACT_SELU = 5, RGNN_ACT_GELU = 6
+};
+/* utils/utils.py:23-33 get_aggregation_function */
+enum rgnn_aggregation { RGNN_AGG_SUM = 0, RGNN_AGG_MAX = 1, RGNN_AGG_MEAN = 2, RGNN_AGG_SQRT_N = 3 };
+/* utils/utils.py:10-20 get_gated_unit (LSTM is unusable as the reference calls it: ggnn.py:92) */
+enum rgnn_cell { RGNN_CELL_RNN = 0, RGNN_CELL_GRU = 1 };
+enum rgnn_layer_kind {
+  RGNN_LAYER_RGCN = 0, RGNN_LAYER_GGNN = 1, RGNN_LAYER_RGAT = 2, RGNN_LAYER_FILM = 3,
+  RGNN_LAYER_EDGE_MLP = 4, RGNN_LAYER_RGIN = 5
+};
+
+typedef struct rgnn_plan rgnn_plan_t;
+
+RGNN_API int rgnn_version(void);
+RGNN_API const char* rgnn_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+RGNN_API int64_t rgnn_launch_count(void);
+
+/*
+ * Plan = the batch's graph structure in the layout the kernels want, built once per batch and
+ * reused by every layer and timestep (replaces the per-layer tf.concat of targets + unsorted
+ * segment ids: gnns/rgcn.py:76-78,108-112).  Contents (device): CSR by target over ALL edge
+ * types, incoming edges of a node sorted by (type, original position) -- a stable sort, so
+ * every reduction order is deterministic.
+ *   adjacency_lists : host array of L device pointers, each int32 [E_l, 2]
+ *   num_edges       : host array [L] (E_l may be 0: tasks/ppi_task.py:246-249)
+ */
+RGNN_API int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t num_edge_types,
+                     const int32_t* const* adjacency_lists, const int64_t* num_edges, void* stream);
+RGNN_API int rgnn_plan_destroy(rgnn_plan_t* plan);
+RGNN_API int32_t rgnn_plan_num_nodes(const rgnn_plan_t* plan);
+RGNN_API int32_t rgnn_plan_num_edge_types(const rgnn_plan_t* plan);
+RGNN_API int64_t rgnn_plan_num_edges(const rgnn_plan_t* plan);       /* M = sum_l E_l */
+/* Copy the plan's arrays into caller DEVICE buffers (any may be NULL): seg_off [V+1],
+ * e_src [M], e_type [M], e_orig [M] (position in the type-major concatenation of the inputs). */
+RGNN_API int rgnn_plan_export(const rgnn_plan_t* plan, int32_t* seg_off, int32_t* e_src, int32_t* e_type,
+                     int32_t* e_orig, void* stream);
+
+/* Upper bound of the scratch a forward of `layer_kind` needs.  mlp_layers = number of kernels
+ * in the widest edge/aggregation MLP (0 if none). */
+RGNN_API size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, int32_t d_in, int32_t d_out,
+                            int32_t mlp_layers);
+
+/* ---- gnns/rgcn.py:8-117  sparse_rgcn_layer ------------------------------------------------
+ * edge_weights: host array of L device pointers, kernel [d_in * (1 + use_both), d_out].
+ * num_incoming: [L, V] fp32 or NULL when normalize == 0.  num_timesteps > 1 needs d_in == d_out. */
+RGNN_API int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* node_embeddings, int32_t d_in, int32_t d_out,
+                      const float* const* edge_weights, const float* num_incoming,
+                      int activation, int aggregation, int normalize_by_num_incoming,
+                      int use_both_source_and_target, int num_timesteps,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- gnns/ggnn.py:8-95  sparse_ggnn_layer --------------------------------------------------
+ * cell_kernel [d, 3d] (GRU, gates z|r|h) or [d, d] (RNN); cell_recurrent_kernel same shape;
+ * cell_bias [3d] / [d].  d_in must equal d_out (the cell state is the node state: ggnn.py:92). */
+RGNN_API int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* node_embeddings, int32_t d_in, int32_t d_out,
+                      const float* const* edge_weights, const float* cell_kernel,
+                      const float* cell_recurrent_kernel, const float* cell_bias,
+                      int cell_kind, int activation, int aggregation, int num_timesteps,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- gnns/rgat.py:9-141  sparse_rgat_layer -------------------------------------------------
+ * attention: host array of L device pointers [2 * d_out]; head k uses [k*2d, (k+1)*2d),
+ * first d for the source, next d for the target (rgat.py:110-111), d = d_out / num_heads. */
+RGNN_API int rgnn_rgat_forward(const rgnn_plan_t* plan, const float* node_embeddings, int32_t d_in, int32_t d_out,
+                      const float* const* edge_weights, const float* const* attention,
+                      int num_heads, int activation, int num_timesteps,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- gnns/gnn_film.py:8-122  sparse_gnn_film_layer -----------------------------------------
+ * film_weights: L pointers, kernel [d_in, 2*d_out] (gamma = cols [0,d), beta = cols [d,2d)).
+ * ln_gamma / ln_beta: [num_timesteps, d_out] (one LayerNorm scope per timestep: gnn_film.py:120). */
+RGNN_API int rgnn_film_forward(const rgnn_plan_t* plan, const float* node_embeddings, int32_t d_in, int32_t d_out,
+                      const float* const* edge_weights, const float* const* film_weights,
+                      const float* num_incoming, const float* ln_gamma, const float* ln_beta,
+                      int activation, int aggregation, int normalize_by_num_incoming, int num_timesteps,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- gnns/gnn_edge_mlp.py:7-122  sparse_gnn_edge_mlp_layer ---------------------------------
+ * mlp_kernels: host array of L * (num_edge_hidden_layers + 1) device pointers, type-major;
+ * layer j of every type has shape [mlp_dims[j], mlp_dims[j+1]]; mlp_dims host [layers + 1],
+ * mlp_dims[0] = d_in * (1 + use_target_state_as_input), mlp_dims[last] = d_out.
+ * Hidden activation is ELU regardless of `activation` (gnn_edge_mlp.py:76). */
+RGNN_API int rgnn_edge_mlp_forward(const rgnn_plan_t* plan, const float* node_embeddings, int32_t d_in, int32_t d_out,
+                          const float* const* mlp_kernels, const int32_t* mlp_dims, int num_edge_hidden_layers,
+                          const float* num_incoming, const float* ln_gamma, const float* ln_beta,
+                          int activation, int aggregation, int normalize_by_num_incoming,
+                          int use_target_state_as_input, int num_timesteps,
+                          float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- gnns/rgin.py:7-142  sparse_rgin_layer -------------------------------------------------
+ * num_edge_mlp_hidden_layers < 0  <=>  None (messages are the raw source states, no activation).
+ * num_aggr_mlp_hidden_layers < 0  <=>  None.  aggr_kernels: host array of (layers+1) pointers,
+ * aggr_dims host [layers + 2].  Edge-MLP hidden activation = `activation` (rgin.py:95). */
+RGNN_API int rgnn_rgin_forward(const rgnn_plan_t* plan, const float* node_embeddings, int32_t d_in, int32_t d_out,
+                      const float* const* edge_mlp_kernels, const int32_t* edge_mlp_dims,
+                      int num_edge_mlp_hidden_layers,
+                      const float* const* aggr_kernels, const int32_t* aggr_dims,
+                      int num_aggr_mlp_hidden_layers,
+                      const float* ln_gamma, const float* ln_beta,
+                      int activation, int aggregation, int use_target_state_as_input, int num_timesteps,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- building blocks exported for tests / other hosts ---------------------------------------
+ * utils/utils.py:23-33: aggregate `data` [M, d] (rows in the ORIGINAL type-major message order)
+ * to [V, d] with the plan's segments -- the tf.unsorted_segment_<agg> call of rgcn.py:110. */
+RGNN_API int rgnn_segment_aggregate(const rgnn_plan_t* plan, const float* data, int32_t d, int aggregation,
+                           float* out, void* stream);
+/* C[M,N] = act(A[M,K] . B[K,N] + bias) on the tensor cores with 3xTF32 split accumulation
+ * (fp32-accurate); the node-level Dense of every layer (A.1). bias may be NULL. */
+RGNN_API int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const float* b, int32_t n,
+                       const float* bias, int activation, float* c, void* stream);
+/* tf.contrib.layers.layer_norm over the last axis, eps 1e-12 (A.5). */
+RGNN_API int rgnn_layer_norm(const float* x, int32_t rows, int32_t d, const float* gamma, const float* beta,
+                    float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGNN_H_ */

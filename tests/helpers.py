@@ -1,0 +1,48 @@
+"""Shared helpers of the parity tests: seeded inputs, oracle call, tolerance."""
+import numpy as np
+
+from oracle import ref_layers as R
+from tf_gnn_samples_b200 import batching, weights as W
+
+TOL = 1e-4   # north-star tolerance: max-norm relative error of fp32 outputs vs the reference path
+
+
+def tiny_graph(num_nodes=37, num_edges=(60, 0, 45, 11), seed=0, with_isolated=True, duplicates=True):
+    """Small multigraph with the edge cases the reference's data paths produce:
+    an empty edge type, isolated targets, duplicate edges, self loops, unsorted targets."""
+    rng = np.random.default_rng(seed)
+    hi = num_nodes - 3 if with_isolated else num_nodes       # last 3 nodes never appear as targets
+    adj = []
+    for e in num_edges:
+        src = rng.integers(0, num_nodes, size=e)
+        tgt = rng.integers(0, hi, size=e)
+        a = np.stack([src, tgt], axis=1).astype(np.int32)
+        if duplicates and e >= 4:
+            a[1] = a[0]
+            a[3] = a[2][::-1]
+        adj.append(a.reshape(-1, 2))
+    indeg = np.stack([np.bincount(a[:, 1], minlength=num_nodes) for a in adj]).astype(np.float32)
+    return adj, indeg
+
+
+def node_states(num_nodes, dim, seed=1):
+    return np.tanh(np.random.default_rng(seed).standard_normal((num_nodes, dim))).astype(np.float32)
+
+
+def assert_parity(got, want64, what="", tol=TOL):
+    got = np.asarray(got, dtype=np.float64)
+    want64 = np.asarray(want64, dtype=np.float64)
+    assert got.shape == want64.shape, "%s: shape %s vs %s" % (what, got.shape, want64.shape)
+    assert np.all(np.isfinite(got)), "%s: non-finite output" % what
+    err = R.max_norm_rel_err(got, want64)
+    assert err <= tol, "%s: max-norm relative error %.3e > %.1e" % (what, err, tol)
+    scale = float(np.max(np.abs(want64))) if want64.size else 1.0
+    assert np.allclose(got, want64, rtol=tol, atol=tol * max(scale, 1e-30)), "%s: allclose failed" % what
+    return err
+
+
+def to_cuda_inputs(h, adj, indeg, device):
+    import torch
+    return (torch.as_tensor(h).to(device),
+            [torch.as_tensor(a).to(device) for a in adj],
+            None if indeg is None else torch.as_tensor(indeg).to(device))

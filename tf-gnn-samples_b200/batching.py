@@ -1,0 +1,163 @@
+"""Batch construction: the host-side tensor contract the hot path consumes.
+
+Mirrors the reference's task batchers (tasks/ppi_task.py:197-256, tasks/qm9_task.py:200-261,
+tasks/varmisuse_task.py:451-538): graphs are packed into one block-diagonal graph by offsetting
+node ids, per-type adjacency lists are concatenated, in-degrees are concatenated along axis 1.
+The reference's datasets are not shipped (data/ppi, data/varmisuse) or not available on the GPU
+box (data/qm9), so the generators below produce seeded, shape-matched synthetic graphs
+(SURVEY.md 8d / Appendix B).  Everything here is numpy on the host, like the reference.
+"""
+from typing import Dict, List, NamedTuple, Optional, Sequence
+
+import numpy as np
+
+
+class GraphSample(NamedTuple):
+    """tasks/ppi_task.py:19-23 (without the labels, which belong to the task head, not the hot path)."""
+    adjacency_lists: List[np.ndarray]                      # L x int32 [E_l, 2], (src, tgt), node ids local to the graph
+    type_to_node_to_num_incoming_edges: np.ndarray         # [L, V_graph]
+    node_features: np.ndarray                              # [V_graph, D0] float32
+
+
+class Batch(NamedTuple):
+    """What a reference MinibatchData feed_dict carries for the GNN layers (tasks/sparse_graph_task.py:139-149)."""
+    node_features: np.ndarray                              # float32 [V, D0]
+    adjacency_lists: List[np.ndarray]                      # L x int32 [E_l, 2]
+    type_to_num_incoming_edges: np.ndarray                 # float32 [L, V]
+    num_graphs: int
+    num_nodes: int
+    num_edges: int                                         # sum_l E_l: the reference's edges/sec counter (sparse_graph_model.py:285)
+    graph_node_offsets: np.ndarray                         # int64 [num_graphs + 1]
+
+
+def _in_degrees(adj: Sequence[np.ndarray], num_nodes: int) -> np.ndarray:
+    return np.stack([np.bincount(a[:, 1], minlength=num_nodes) if a.shape[0] else np.zeros(num_nodes, np.int64)
+                     for a in adj]).astype(np.int32)
+
+
+def make_ppi_like_graph(num_nodes: int = 2245, num_links: int = 59000, feature_dim: int = 50, seed: int = 0,
+                        zipf_targets: bool = False) -> GraphSample:
+    """One PPI-shaped graph with the reference's three edge types: 0 = fwd (u,v), 1 = self-loop (i,i),
+    2 = bkwd (v,u)  (tasks/ppi_task.py:99-106,125-127,144-148; add_self_loop_edges=True,
+    tie_fwd_bkwd_edges=False).  Links are i.i.d. uniform (or Zipf(1.0)-skewed targets)."""
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, num_nodes, size=num_links, dtype=np.int64)
+    if zipf_targets:
+        p = 1.0 / np.arange(1, num_nodes + 1)
+        p /= p.sum()
+        tgt = rng.choice(num_nodes, size=num_links, p=p).astype(np.int64)
+        tgt = rng.permutation(num_nodes)[tgt]          # hubs are not the low ids
+    else:
+        tgt = rng.integers(0, num_nodes, size=num_links, dtype=np.int64)
+    fwd = np.stack([src, tgt], axis=1).astype(np.int32)
+    loops = np.stack([np.arange(num_nodes), np.arange(num_nodes)], axis=1).astype(np.int32)
+    bkwd = np.stack([tgt, src], axis=1).astype(np.int32)
+    adj = [fwd, loops, bkwd]
+    feats = rng.standard_normal((num_nodes, feature_dim)).astype(np.float32)
+    return GraphSample(adj, _in_degrees(adj, num_nodes), feats)
+
+
+def make_qm9_like_graph(rng: np.random.Generator, feature_dim: int = 15, add_self_loop_edges: bool = False) -> GraphSample:
+    """One molecule-shaped graph (QM9 statistics measured in SURVEY.md Appendix B: 3..29 nodes, mean 18,
+    ~1.03 bonds per node, bond types 1-4) laid out like tasks/qm9_task.py:114-147 with
+    tie_fwd_bkwd_edges=True: both directions of a bond live in the bond's type, adjacency sorted by (src, dst)."""
+    n = int(np.clip(round(rng.normal(18.0, 3.0)), 3, 29))
+    edges = []
+    for v in range(1, n):                                   # random spanning tree
+        edges.append((int(rng.integers(0, v)), v))
+    for _ in range(max(0, int(round(0.035 * n + rng.random())))):   # a few ring closures
+        a, b = int(rng.integers(0, n)), int(rng.integers(0, n))
+        if a != b:
+            edges.append((a, b))
+    num_types = 4 + (1 if add_self_loop_edges else 0)
+    shift = 1 if add_self_loop_edges else 0
+    per_type = [[] for _ in range(num_types)]
+    if add_self_loop_edges:
+        per_type[0] = [(i, i) for i in range(n)]
+    for (a, b) in edges:
+        t = int(rng.choice(4, p=[0.86, 0.09, 0.03, 0.02])) + shift
+        per_type[t].append((a, b))
+        per_type[t].append((b, a))
+    adj = []
+    for lst in per_type:
+        arr = np.array(sorted(lst), dtype=np.int32).reshape(-1, 2)
+        adj.append(arr)
+    feats = rng.standard_normal((n, feature_dim)).astype(np.float32)
+    return GraphSample(adj, _in_degrees(adj, n), feats)
+
+
+def make_qm9_like_graphs(num_graphs: int, seed: int = 0, add_self_loop_edges: bool = False) -> List[GraphSample]:
+    rng = np.random.default_rng(seed)
+    return [make_qm9_like_graph(rng, add_self_loop_edges=add_self_loop_edges) for _ in range(num_graphs)]
+
+
+def make_typed_random_graph(num_nodes: int, num_edges: int, type_fractions: Sequence[float], feature_dim: int,
+                            seed: int = 0) -> GraphSample:
+    """Uniform random multigraph with the edges split over L types in the given proportions
+    (VarMisuse-shaped config: SURVEY.md 8d config 5)."""
+    rng = np.random.default_rng(seed)
+    fr = np.asarray(type_fractions, dtype=np.float64)
+    counts = np.floor(fr / fr.sum() * num_edges).astype(np.int64)
+    counts[0] += num_edges - counts.sum()
+    adj = []
+    for c in counts:
+        a = np.stack([rng.integers(0, num_nodes, size=int(c)), rng.integers(0, num_nodes, size=int(c))], axis=1)
+        adj.append(a.astype(np.int32))
+    feats = rng.standard_normal((num_nodes, feature_dim)).astype(np.float32)
+    return GraphSample(adj, _in_degrees(adj, num_nodes), feats)
+
+
+def pack_batch(graphs: Sequence[GraphSample], max_nodes_per_batch: Optional[int] = None) -> Batch:
+    """The packing loop of tasks/ppi_task.py:213-251: add graphs while node_offset + |graph| <
+    max_nodes_per_batch, shift node ids by the running offset, concatenate per type; an edge type with no
+    edge in the batch becomes np.zeros((0, 2)) (:246-249)."""
+    num_types = len(graphs[0].adjacency_lists)
+    feats, indeg, offsets = [], [], [0]
+    adj: List[List[np.ndarray]] = [[] for _ in range(num_types)]
+    node_offset = 0
+    for g in graphs:
+        n = g.node_features.shape[0]
+        if max_nodes_per_batch is not None and not (node_offset + n < max_nodes_per_batch):
+            break
+        feats.append(g.node_features)
+        for i in range(num_types):
+            adj[i].append(g.adjacency_lists[i].reshape(-1, 2) + node_offset)
+        indeg.append(g.type_to_node_to_num_incoming_edges)
+        node_offset += n
+        offsets.append(node_offset)
+    merged, num_edges = [], 0
+    for i in range(num_types):
+        a = np.concatenate(adj[i]).astype(np.int32) if len(adj[i]) > 0 else np.zeros((0, 2), dtype=np.int32)
+        num_edges += a.shape[0]
+        merged.append(a)
+    return Batch(node_features=np.concatenate(feats, axis=0).astype(np.float32),
+                 adjacency_lists=merged,
+                 type_to_num_incoming_edges=np.concatenate(indeg, axis=1).astype(np.float32),
+                 num_graphs=len(feats), num_nodes=node_offset, num_edges=num_edges,
+                 graph_node_offsets=np.asarray(offsets, dtype=np.int64))
+
+
+def ppi_like_batch(num_graphs: int = 1, num_nodes: int = 2245, num_links: int = 59000, seed: int = 0,
+                   zipf_targets: bool = False) -> Batch:
+    """BASELINE config 2: one PPI-shaped graph -> V=2,245, M = 2*59,000 + 2,245 = 120,245, L=3."""
+    return pack_batch([make_ppi_like_graph(num_nodes, num_links, seed=seed + i, zipf_targets=zipf_targets)
+                       for i in range(num_graphs)])
+
+
+def qm9_like_batch(num_graphs: int = 10000, seed: int = 0, add_self_loop_edges: bool = False) -> Batch:
+    """BASELINE config 3 shape: 10k molecule graphs, ~18 nodes each, 4 bond types (5 with self loops)."""
+    return pack_batch(make_qm9_like_graphs(num_graphs, seed, add_self_loop_edges))
+
+
+VARMISUSE_TYPE_FRACTIONS = (0.30, 0.30, 0.15, 0.15, 0.05, 0.05)
+
+
+def varmisuse_like_batch(num_nodes: int = 50000, num_edges: int = 1000000, packed_graphs: int = 0, seed: int = 0,
+                         feature_dim: int = 64) -> Batch:
+    """BASELINE config 5 shape: V=50k, M=1M, L=6.  packed_graphs=0 -> one random graph (worst-case halo);
+    packed_graphs=g -> g equal graphs packed block-diagonally (zero-halo partition possible)."""
+    if packed_graphs <= 0:
+        return pack_batch([make_typed_random_graph(num_nodes, num_edges, VARMISUSE_TYPE_FRACTIONS, feature_dim, seed)])
+    n, e = num_nodes // packed_graphs, num_edges // packed_graphs
+    return pack_batch([make_typed_random_graph(n, e, VARMISUSE_TYPE_FRACTIONS, feature_dim, seed + i)
+                       for i in range(packed_graphs)])

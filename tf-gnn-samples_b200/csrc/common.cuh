@@ -1,0 +1,76 @@
+// common.cuh -- shared helpers of librgnn (error plumbing, activations, vector loads).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <float.h>
+#include <math.h>
+
+#include "../../include/rgnn.h"
+
+namespace rgnn {
+
+// ---- error plumbing (thread-local message, never throws across the ABI) ----
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define RGNN_CHECK_CUDA(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      rgnn::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                      cudaGetErrorString(_e));                                             \
+      return RGNN_E_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define RGNN_REQUIRE(cond, ...)                                                            \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      rgnn::set_error(__VA_ARGS__);                                                        \
+      return RGNN_E_INVALID;                                                               \
+    }                                                                                      \
+  } while (0)
+
+#define RGNN_PROPAGATE(expr)                                                               \
+  do {                                                                                     \
+    int _r = (expr);                                                                       \
+    if (_r != RGNN_OK) return _r;                                                          \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device-side activations: utils/utils.py:36-58 ----
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case RGNN_ACT_TANH: return tanhf(x);
+    case RGNN_ACT_RELU: return fmaxf(x, 0.0f);
+    case RGNN_ACT_LEAKY_RELU: return x > 0.0f ? x : 0.2f * x;            // tf.nn.leaky_relu alpha=0.2
+    case RGNN_ACT_ELU: return x > 0.0f ? x : expm1f(x);
+    case RGNN_ACT_SELU: return 1.0507009873554805f * (x > 0.0f ? x : 1.6732632423543772f * expm1f(x));
+    case RGNN_ACT_GELU: return x * (0.5f * (1.0f + erff(x * 0.70710678118654752f)));  // exact-erf form
+    default: return x;                                                    // linear / None
+  }
+}
+__device__ __forceinline__ float hard_sigmoid(float x) {                 // Keras hard_sigmoid (TF1 GRU default)
+  return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f);
+}
+__device__ __forceinline__ float4 act4(float4 v, int act) {
+  if (act == RGNN_ACT_LINEAR) return v;
+  v.x = apply_act(v.x, act); v.y = apply_act(v.y, act);
+  v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+  return v;
+}
+
+// read-only 128-bit load through the non-coherent path (tables written by a previous kernel)
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace rgnn

@@ -1,0 +1,47 @@
+// gemm.cuh -- node-level dense contraction on the tensor cores, fp32-accurate (3xTF32 split).
+#pragma once
+#include "common.cuh"
+
+namespace rgnn {
+
+enum GemmEpilogue {
+  EPI_STORE = 0,    // C = act(acc + bias)
+  EPI_GRU_ZR = 1,   // N = 2d: g = hard_sigmoid(acc + bias); cols [0,d): Z = g ; cols [d,2d): RH = g * h
+  EPI_GRU_OUT = 2,  // N = d : hh = act(acc + bias); C = z*h + (1-z)*hh
+};
+
+enum GemmBatchMode {
+  BATCH_NONE = 0,
+  BATCH_SHARED_A = 1,   // z = type: A shared, B = bptr[z], C columns offset z * N            (T = H . [W_0|..|W_{L-1}])
+  BATCH_ROW_RANGES = 2, // z = type: rows [row_off[z], row_off[z+1]) of A and C, B = bptr[z]   (per-edge MLP layers)
+  BATCH_COL_BLOCKS = 3, // z = type: A columns offset z * K, B = bptr[z], C columns offset z * N (per-node MLP chains)
+};
+
+struct GemmParams {
+  // A = [A1 | A2] along K (A2 optional, K2 = 0 when absent); B = [B1 ; B2] along K
+  const float* A1 = nullptr; int lda1 = 0; int K1 = 0;
+  const float* A2 = nullptr; int lda2 = 0; int K2 = 0;
+  const float* B1 = nullptr; int ldb1 = 0;
+  const float* B2 = nullptr; int ldb2 = 0;
+  float* C = nullptr; int ldc = 0;
+  int M = 0, N = 0;
+  const float* bias = nullptr;
+  int epi = EPI_STORE;
+  int act = RGNN_ACT_LINEAR;
+  // epilogue operands (GRU): h [M, d] and z [M, d]; second output RH [M, d]
+  const float* aux_h = nullptr; int ld_h = 0;
+  const float* aux_z = nullptr; int ld_z = 0;
+  float* C2 = nullptr; int ldc2 = 0;
+  // batching over blockIdx.z
+  int batch_mode = BATCH_NONE;
+  int batch = 1;
+  const float* bptr[RGNN_MAX_EDGE_TYPES];     // per-batch B1 (row offset for B2-style splits handled by caller)
+  const float* bptr2[RGNN_MAX_EDGE_TYPES];    // per-batch B2 (optional)
+  int row_off[RGNN_MAX_EDGE_TYPES + 1];       // BATCH_ROW_RANGES
+  int max_rows = 0;                           // max rows of any batch entry (grid sizing)
+};
+
+// Enqueue; returns RGNN_OK / error code.  All dims % 4 == 0, pointers 16-byte aligned.
+int launch_gemm(const GemmParams& p, cudaStream_t stream);
+
+}  // namespace rgnn

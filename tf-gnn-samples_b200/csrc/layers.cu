@@ -1,0 +1,588 @@
+// layers.cu -- C-ABI entry points: one forward per reference layer function (include/rgnn.h).
+//
+// Every layer is re-associated "transform first" (SURVEY.md 7): the per-type Dense is applied to the
+// V node rows (one tensor-core GEMM over all types, T = H . [W_0|...|W_{L-1}]) instead of to the M
+// gathered edge rows (gnns/rgcn.py:88,98 does M*D*D*2 FLOP; this does V*L*D*D*2), and the edge stage
+// is one fused sorted-segment kernel (seg_kernels.cu).  RGAT already works this way in the reference
+// (rgat.py:95-96).  Only an MLP's layers after a per-edge nonlinearity stay per-edge (edge-MLP with
+// >= 1 hidden layer and target input): those run as per-type row-range GEMMs over materialised rows.
+#include <mutex>
+#include <atomic>
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "plan.cuh"
+#include "seg.cuh"
+
+namespace rgnn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base;
+  size_t cap, used = 0;
+  bool overflow = false;
+  Arena(void* b, size_t c) : base(static_cast<char*>(b)), cap(c) {}
+  float* floats(size_t n) {
+    const size_t bytes = align_up(n * sizeof(float), 256);
+    if (base == nullptr || used + bytes > cap) { overflow = true; used += bytes; return nullptr; }
+    float* p = reinterpret_cast<float*>(base + used);
+    used += bytes;
+    return p;
+  }
+};
+
+int check_common(const rgnn_plan_t* plan, const float* h, int d_in, int d_out, const float* out, int num_timesteps,
+                 const char* who) {
+  RGNN_REQUIRE(plan != nullptr, "%s: plan is NULL", who);
+  RGNN_REQUIRE(h != nullptr && out != nullptr, "%s: node_embeddings / out is NULL", who);
+  RGNN_REQUIRE(h != out, "%s: out must not alias node_embeddings", who);
+  RGNN_REQUIRE(aligned16(h) && aligned16(out), "%s: node_embeddings / out must be 16-byte aligned", who);
+  RGNN_REQUIRE(d_in > 0 && d_out > 0 && (d_in % 4) == 0 && (d_out % 4) == 0,
+               "%s: state dims must be positive multiples of 4 (d_in=%d, d_out=%d)", who, d_in, d_out);
+  RGNN_REQUIRE(num_timesteps >= 1, "%s: num_timesteps %d < 1", who, num_timesteps);
+  RGNN_REQUIRE(num_timesteps == 1 || d_in == d_out,
+               "%s: num_timesteps > 1 needs state_dim == input dim (d_in=%d, d_out=%d)", who, d_in, d_out);
+  return RGNN_OK;
+}
+int check_act(int act, const char* who) {
+  RGNN_REQUIRE(act >= RGNN_ACT_LINEAR && act <= RGNN_ACT_GELU, "%s: Unknown activation function code %d", who, act);
+  return RGNN_OK;
+}
+int check_agg(int agg, const char* who) {
+  RGNN_REQUIRE(agg >= RGNN_AGG_SUM && agg <= RGNN_AGG_SQRT_N, "%s: Unknown aggregation function code %d", who, agg);
+  return RGNN_OK;
+}
+int check_ws(const Arena& a, const char* who) {
+  if (a.overflow) {
+    set_error("%s: workspace too small (%zu bytes given, %zu needed)", who, a.cap, a.used);
+    return RGNN_E_WORKSPACE;
+  }
+  return RGNN_OK;
+}
+
+// T[V, batch*N] = A[V, K] . B_z  for z < batch  (shared A)
+int gemm_shared_a(const float* A, int V, int K, const float* const* B, int batch, int ldb, int N, float* C, int act,
+                  cudaStream_t stream) {
+  GemmParams g;
+  g.A1 = A; g.lda1 = K; g.K1 = K;
+  g.M = V; g.N = N;
+  g.C = C; g.ldc = batch * N;
+  g.ldb1 = ldb;
+  g.act = act;
+  g.batch_mode = BATCH_SHARED_A; g.batch = batch;
+  for (int z = 0; z < batch; ++z) { g.bptr[z] = B[z]; g.bptr2[z] = nullptr; }
+  return launch_gemm(g, stream);
+}
+
+void seg_from_plan(SegParams& s, const rgnn_plan_t* plan) {
+  s.V = plan->V; s.L = plan->L;
+  s.seg_off = plan->seg_off; s.e_type = plan->e_type; s.e_idx = plan->e_src;
+}
+
+// Where the per-message rows of an MLP-style layer live after the dense stages.
+struct MsgSource {
+  const float* table = nullptr;
+  const int32_t* idx = nullptr;
+  long stride_idx = 0, stride_type = 0;
+  int width = 0;
+  int msg_mode = MSG_LINEAR;
+  const float* mod_table = nullptr;
+  long mod_sn = 0, mod_st = 0;
+};
+
+// Evaluate MLP_l([h_u | h_v]) / MLP_l(h_u) for every message (gnn_edge_mlp.py:87-102, rgin.py:106-124).
+// kernels: type-major [L][nl]; dims [nl+1]; nl = number of Dense kernels (hidden layers + 1), 0 = no MLP.
+int build_mlp_messages(const rgnn_plan_t* plan, const float* cur, int d_in, const float* const* kernels,
+                       const int32_t* dims, int nl, int use_target, int hidden_act, Arena& ar, cudaStream_t stream,
+                       MsgSource* out) {
+  const int V = plan->V, L = plan->L;
+  const int M = (int)plan->M;
+  MsgSource ms;
+  if (nl == 0) {
+    if (!use_target) {
+      ms.table = cur; ms.idx = plan->e_src; ms.stride_idx = d_in; ms.stride_type = 0; ms.width = d_in;
+    } else {   // messages are the raw [h_u | h_v] pairs (rgin.py:114-124 with edge MLP None)
+      float* X = ar.floats((size_t)M * 2 * d_in);
+      if (ar.overflow) { *out = ms; return RGNN_OK; }
+      EdgeBuildParams b;
+      b.L = L; b.D = d_in; b.o_src = plan->o_src; b.o_tgt = plan->o_tgt;
+      memcpy(b.type_off, plan->type_off, sizeof(b.type_off)); b.max_type_edges = plan->max_type_edges;
+      b.p = cur; b.p_stride_node = d_in; b.p_stride_type = 0; b.concat = 1;
+      b.x = X; b.ldx = 2 * d_in;
+      RGNN_PROPAGATE(launch_edge_build(b, stream));
+      ms.table = X; ms.idx = plan->e_orig; ms.stride_idx = 2 * d_in; ms.stride_type = 0; ms.width = 2 * d_in;
+    }
+    *out = ms;
+    return RGNN_OK;
+  }
+  RGNN_REQUIRE(nl <= RGNN_MAX_MLP_LAYERS, "edge MLP with %d layers exceeds the supported %d", nl, RGNN_MAX_MLP_LAYERS);
+  RGNN_REQUIRE(dims[0] == d_in * (use_target ? 2 : 1), "edge MLP input dim %d does not match %d", dims[0],
+               d_in * (use_target ? 2 : 1));
+  for (int j = 1; j <= nl; ++j) RGNN_REQUIRE(dims[j] > 0 && (dims[j] % 4) == 0, "edge MLP dim %d must be a positive multiple of 4", dims[j]);
+  for (int i = 0; i < L * nl; ++i) RGNN_REQUIRE(kernels[i] != nullptr, "edge MLP kernel %d is NULL", i);
+
+  const float* bp[RGNN_MAX_EDGE_TYPES];
+  if (!use_target) {
+    // whole MLP is per (node, type): chain of node-level GEMMs
+    float* prev = ar.floats((size_t)V * L * dims[1]);
+    if (ar.overflow) { *out = ms; return RGNN_OK; }
+    for (int l = 0; l < L; ++l) bp[l] = kernels[l * nl + 0];
+    RGNN_PROPAGATE(gemm_shared_a(cur, V, d_in, bp, L, dims[1], dims[1], prev, nl > 1 ? hidden_act : RGNN_ACT_LINEAR, stream));
+    for (int j = 1; j < nl; ++j) {
+      float* next = ar.floats((size_t)V * L * dims[j + 1]);
+      if (ar.overflow) { *out = ms; return RGNN_OK; }
+      GemmParams g;
+      g.A1 = prev; g.lda1 = L * dims[j]; g.K1 = dims[j];
+      g.M = V; g.N = dims[j + 1]; g.C = next; g.ldc = L * dims[j + 1]; g.ldb1 = dims[j + 1];
+      g.act = (j < nl - 1) ? hidden_act : RGNN_ACT_LINEAR;
+      g.batch_mode = BATCH_COL_BLOCKS; g.batch = L;
+      for (int l = 0; l < L; ++l) { g.bptr[l] = kernels[l * nl + j]; g.bptr2[l] = nullptr; }
+      RGNN_PROPAGATE(launch_gemm(g, stream));
+      prev = next;
+    }
+    ms.table = prev; ms.idx = plan->e_src; ms.stride_idx = (long)L * dims[nl]; ms.stride_type = dims[nl]; ms.width = dims[nl];
+    *out = ms;
+    return RGNN_OK;
+  }
+  // use_target: first Dense splits into a source half P and a target half Q of the kernel rows
+  RGNN_REQUIRE(2 * L <= RGNN_MAX_EDGE_TYPES, "edge MLP with target input supports at most %d edge types", RGNN_MAX_EDGE_TYPES / 2);
+  const int d1 = dims[1];
+  float* PQ = ar.floats((size_t)V * 2 * L * d1);
+  if (ar.overflow) { *out = ms; return RGNN_OK; }
+  for (int l = 0; l < L; ++l) {
+    bp[l] = kernels[l * nl + 0];                              // rows [0, d_in)      multiply h_u
+    bp[L + l] = kernels[l * nl + 0] + (size_t)d_in * d1;      // rows [d_in, 2 d_in) multiply h_v
+  }
+  RGNN_PROPAGATE(gemm_shared_a(cur, V, d_in, bp, 2 * L, d1, d1, PQ, RGNN_ACT_LINEAR, stream));
+  if (nl == 1) {
+    ms.table = PQ; ms.idx = plan->e_src; ms.stride_idx = 2L * L * d1; ms.stride_type = d1; ms.width = d1;
+    ms.msg_mode = MSG_ADDTGT; ms.mod_table = PQ + (size_t)L * d1; ms.mod_sn = 2L * L * d1; ms.mod_st = d1;
+    *out = ms;
+    return RGNN_OK;
+  }
+  float* X = ar.floats((size_t)M * d1);
+  if (ar.overflow) { *out = ms; return RGNN_OK; }
+  {
+    EdgeBuildParams b;
+    b.L = L; b.D = d1; b.o_src = plan->o_src; b.o_tgt = plan->o_tgt;
+    memcpy(b.type_off, plan->type_off, sizeof(b.type_off)); b.max_type_edges = plan->max_type_edges;
+    b.p = PQ; b.p_stride_node = 2L * L * d1; b.p_stride_type = d1;
+    b.q = PQ + (size_t)L * d1; b.q_stride_node = 2L * L * d1; b.q_stride_type = d1;
+    b.act = hidden_act; b.x = X; b.ldx = d1;
+    RGNN_PROPAGATE(launch_edge_build(b, stream));
+  }
+  float* prev = X;
+  for (int j = 1; j < nl; ++j) {
+    float* next = ar.floats((size_t)M * dims[j + 1]);
+    if (ar.overflow) { *out = ms; return RGNN_OK; }
+    GemmParams g;
+    g.A1 = prev; g.lda1 = dims[j]; g.K1 = dims[j];
+    g.M = M; g.N = dims[j + 1]; g.C = next; g.ldc = dims[j + 1]; g.ldb1 = dims[j + 1];
+    g.act = (j < nl - 1) ? hidden_act : RGNN_ACT_LINEAR;
+    g.batch_mode = BATCH_ROW_RANGES; g.batch = L; g.max_rows = plan->max_type_edges;
+    for (int l = 0; l < L; ++l) { g.bptr[l] = kernels[l * nl + j]; g.bptr2[l] = nullptr; g.row_off[l] = plan->type_off[l]; }
+    g.row_off[L] = plan->type_off[L];
+    RGNN_PROPAGATE(launch_gemm(g, stream));
+    prev = next;
+  }
+  ms.table = prev; ms.idx = plan->e_orig; ms.stride_idx = dims[nl]; ms.stride_type = 0; ms.width = dims[nl];
+  *out = ms;
+  return RGNN_OK;
+}
+
+void seg_from_source(SegParams& s, const MsgSource& ms) {
+  s.table = ms.table; s.e_idx = ms.idx; s.stride_idx = ms.stride_idx; s.stride_type = ms.stride_type;
+  s.D = ms.width; s.msg_mode = ms.msg_mode; s.mod_table = ms.mod_table;
+  s.mod_stride_node = ms.mod_sn; s.mod_stride_type = ms.mod_st;
+}
+
+}  // namespace
+}  // namespace rgnn
+
+using namespace rgnn;
+
+extern "C" int rgnn_version(void) { return RGNN_VERSION; }
+extern "C" const char* rgnn_last_error(void) { return g_err; }
+extern "C" int64_t rgnn_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, int32_t d_in, int32_t d_out,
+                                       int32_t mlp_layers) {
+  if (plan == nullptr || d_in <= 0 || d_out <= 0) return 0;
+  const size_t V = (size_t)plan->V, L = (size_t)plan->L, M = (size_t)plan->M;
+  const size_t dm = (size_t)((2 * d_in > d_out) ? 2 * d_in : d_out);
+  const size_t pad = 256 * 32;
+  size_t floats = 0;
+  switch (layer_kind) {
+    case RGNN_LAYER_RGCN: floats = V * 2 * L * dm + 2 * V * dm; break;
+    case RGNN_LAYER_GGNN: floats = V * L * dm + 6 * V * dm; break;
+    case RGNN_LAYER_RGAT: floats = V * L * dm + 2 * V * L * dm / 4 + 2 * V * dm; break;
+    case RGNN_LAYER_FILM: floats = 3 * V * L * dm + 2 * V * dm; break;
+    case RGNN_LAYER_EDGE_MLP:
+    case RGNN_LAYER_RGIN: {
+      const size_t nl = (size_t)(mlp_layers > 0 ? mlp_layers : 1);
+      floats = V * 2 * L * dm * (nl + 1) + M * dm * (nl + 1) + (4 + nl) * V * dm;
+      break;
+    }
+    default: return 0;
+  }
+  return floats * sizeof(float) + pad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gnns/rgcn.py:8-117
+// ---------------------------------------------------------------------------------------------
+extern "C" int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* h, int32_t d_in, int32_t d_out,
+                                 const float* const* edge_weights, const float* num_incoming, int activation,
+                                 int aggregation, int normalize, int both, int num_timesteps, float* out,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "rgcn"));
+  RGNN_PROPAGATE(check_act(activation, "rgcn"));
+  RGNN_PROPAGATE(check_agg(aggregation, "rgcn"));
+  RGNN_REQUIRE(edge_weights != nullptr, "rgcn: edge_weights is NULL");
+  RGNN_REQUIRE(!normalize || num_incoming != nullptr, "rgcn: normalize_by_num_incoming needs type_to_num_incoming_edges");
+  const int V = plan->V, L = plan->L;
+  RGNN_REQUIRE(!both || 2 * L <= RGNN_MAX_EDGE_TYPES, "rgcn: use_both_source_and_target supports at most %d edge types", RGNN_MAX_EDGE_TYPES / 2);
+  for (int l = 0; l < L; ++l) RGNN_REQUIRE(edge_weights[l] != nullptr, "rgcn: edge weight %d is NULL", l);
+  Arena ar(workspace, workspace_bytes);
+  const int nb = both ? 2 * L : L;
+  float* T = ar.floats((size_t)V * nb * d_out);
+  float* buf[2] = {nullptr, nullptr};
+  if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * d_out); buf[1] = ar.floats((size_t)V * d_out); }
+  RGNN_PROPAGATE(check_ws(ar, "rgcn"));
+
+  const float* bp[RGNN_MAX_EDGE_TYPES];
+  const float* cur = h;
+  int din = d_in;
+  for (int t = 0; t < num_timesteps; ++t) {                                   // rgcn.py:81
+    float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
+    for (int l = 0; l < L; ++l) {
+      bp[l] = edge_weights[l];                                                // kernel rows [0, d_in): source half
+      if (both) bp[L + l] = edge_weights[l] + (size_t)din * d_out;            // rows [d_in, 2 d_in): target half (rgcn.py:95)
+    }
+    RGNN_PROPAGATE(gemm_shared_a(cur, V, din, bp, nb, d_out, d_out, T, RGNN_ACT_LINEAR, stream));   // rgcn.py:98 on nodes
+    SegParams s;
+    seg_from_plan(s, plan);
+    s.D = d_out; s.table = T; s.stride_idx = (long)nb * d_out; s.stride_type = d_out;
+    s.num_incoming = normalize ? num_incoming : nullptr;                      // rgcn.py:100-104
+    if (both) { s.msg_mode = MSG_ADDTGT; s.mod_table = T + (size_t)L * d_out; s.mod_stride_node = (long)nb * d_out; s.mod_stride_type = d_out; }
+    s.agg = aggregation; s.act_out = activation;                              // rgcn.py:110,114
+    s.out = dst; s.ld_out = d_out;
+    RGNN_PROPAGATE(launch_seg_reduce(s, stream));
+    cur = dst; din = d_out;
+  }
+  return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gnns/ggnn.py:8-95
+// ---------------------------------------------------------------------------------------------
+extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_t d_in, int32_t d_out,
+                                 const float* const* edge_weights, const float* cell_kernel,
+                                 const float* cell_recurrent_kernel, const float* cell_bias, int cell_kind,
+                                 int activation, int aggregation, int num_timesteps, float* out, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "ggnn"));
+  RGNN_PROPAGATE(check_act(activation, "ggnn"));
+  RGNN_PROPAGATE(check_agg(aggregation, "ggnn"));
+  RGNN_REQUIRE(d_in == d_out, "ggnn: the recurrent cell needs state_dim == input dim (d_in=%d, d_out=%d)", d_in, d_out);
+  if (cell_kind != RGNN_CELL_RNN && cell_kind != RGNN_CELL_GRU) {
+    set_error("Unknown RNN cell type code %d.", cell_kind);                   // utils/utils.py:20
+    return RGNN_E_INVALID;
+  }
+  RGNN_REQUIRE(edge_weights && cell_kernel && cell_recurrent_kernel && cell_bias, "ggnn: NULL weight pointer");
+  RGNN_REQUIRE(aligned16(cell_kernel) && aligned16(cell_recurrent_kernel), "ggnn: cell kernels must be 16-byte aligned");
+  const int V = plan->V, L = plan->L, D = d_out;
+  for (int l = 0; l < L; ++l) RGNN_REQUIRE(edge_weights[l] != nullptr, "ggnn: edge weight %d is NULL", l);
+  Arena ar(workspace, workspace_bytes);
+  float* T = ar.floats((size_t)V * L * D);
+  float* m = ar.floats((size_t)V * D);
+  float* z = ar.floats((size_t)V * D);
+  float* rh = ar.floats((size_t)V * D);
+  float* buf[2] = {ar.floats((size_t)V * D), ar.floats((size_t)V * D)};
+  RGNN_PROPAGATE(check_ws(ar, "ggnn"));
+
+  const float* cur = h;
+  for (int t = 0; t < num_timesteps; ++t) {                                   // ggnn.py:71
+    float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
+    RGNN_PROPAGATE(gemm_shared_a(cur, V, D, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));   // ggnn.py:80-82
+    SegParams s;
+    seg_from_plan(s, plan);
+    s.D = D; s.table = T; s.stride_idx = (long)L * D; s.stride_type = D;
+    s.agg = aggregation; s.out = m; s.ld_out = D;                             // ggnn.py:87-90
+    RGNN_PROPAGATE(launch_seg_reduce(s, stream));
+    GemmParams g;
+    g.A1 = m; g.lda1 = D; g.K1 = D;
+    g.M = V; g.bias = cell_bias;
+    if (cell_kind == RGNN_CELL_RNN) {                                         // SimpleRNNCell: act(x.W + b + h.U)
+      g.A2 = cur; g.lda2 = D; g.K2 = D;
+      g.B1 = cell_kernel; g.ldb1 = D; g.B2 = cell_recurrent_kernel; g.ldb2 = D;
+      g.N = D; g.C = dst; g.ldc = D; g.epi = EPI_STORE; g.act = activation;
+      RGNN_PROPAGATE(launch_gemm(g, stream));
+    } else {                                                                  // GRUCell, gates z|r|h (A.4)
+      g.A2 = cur; g.lda2 = D; g.K2 = D;
+      g.B1 = cell_kernel; g.ldb1 = 3 * D; g.B2 = cell_recurrent_kernel; g.ldb2 = 3 * D;
+      g.N = 2 * D; g.C = z; g.ldc = D; g.C2 = rh; g.ldc2 = D; g.aux_h = cur; g.ld_h = D;
+      g.epi = EPI_GRU_ZR;
+      RGNN_PROPAGATE(launch_gemm(g, stream));
+      GemmParams o;
+      o.A1 = m; o.lda1 = D; o.K1 = D; o.A2 = rh; o.lda2 = D; o.K2 = D;
+      o.B1 = cell_kernel + 2 * D; o.ldb1 = 3 * D; o.B2 = cell_recurrent_kernel + 2 * D; o.ldb2 = 3 * D;
+      o.M = V; o.N = D; o.bias = cell_bias + 2 * D; o.C = dst; o.ldc = D;
+      o.aux_h = cur; o.ld_h = D; o.aux_z = z; o.ld_z = D;
+      o.epi = EPI_GRU_OUT; o.act = activation;
+      RGNN_PROPAGATE(launch_gemm(o, stream));
+    }
+    cur = dst;
+  }
+  return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gnns/rgat.py:9-141
+// ---------------------------------------------------------------------------------------------
+extern "C" int rgnn_rgat_forward(const rgnn_plan_t* plan, const float* h, int32_t d_in, int32_t d_out,
+                                 const float* const* edge_weights, const float* const* attention, int num_heads,
+                                 int activation, int num_timesteps, float* out, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "rgat"));
+  RGNN_PROPAGATE(check_act(activation, "rgat"));
+  RGNN_REQUIRE(edge_weights != nullptr && attention != nullptr, "rgat: NULL weight table");
+  RGNN_REQUIRE(num_heads >= 1 && (d_out % num_heads) == 0, "rgat: state_dim %d not divisible by num_heads %d", d_out, num_heads);
+  const int V = plan->V, L = plan->L, D = d_out, K = num_heads;
+  AttnTable at;
+  for (int l = 0; l < L; ++l) {
+    RGNN_REQUIRE(edge_weights[l] != nullptr && attention[l] != nullptr && aligned16(attention[l]), "rgat: weight %d is NULL / misaligned", l);
+    at.att[l] = attention[l];
+  }
+  Arena ar(workspace, workspace_bytes);
+  float* T = ar.floats((size_t)V * L * D);
+  float* ssrc = ar.floats((size_t)V * L * K);
+  float* stgt = ar.floats((size_t)V * L * K);
+  float* buf[2] = {nullptr, nullptr};
+  if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * D); buf[1] = ar.floats((size_t)V * D); }
+  RGNN_PROPAGATE(check_ws(ar, "rgat"));
+
+  const float* cur = h;
+  int din = d_in;
+  for (int t = 0; t < num_timesteps; ++t) {                                   // rgat.py:83
+    float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
+    RGNN_PROPAGATE(gemm_shared_a(cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));   // rgat.py:95-96
+    RGNN_PROPAGATE(launch_rgat_scores(T, V, L, D, K, at, ssrc, stgt, stream));                      // rgat.py:106-115 (per node)
+    RgatParams r;
+    r.V = V; r.L = L; r.D = D; r.K = K;
+    r.seg_off = plan->seg_off; r.e_src = plan->e_src; r.e_type = plan->e_type;
+    r.table = T; r.s_src = ssrc; r.s_tgt = stgt; r.act_out = activation; r.out = dst;
+    RGNN_PROPAGATE(launch_seg_rgat(r, stream));                                                      // rgat.py:120-138
+    cur = dst; din = D;
+  }
+  return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gnns/gnn_film.py:8-122
+// ---------------------------------------------------------------------------------------------
+extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_t d_in, int32_t d_out,
+                                 const float* const* edge_weights, const float* const* film_weights,
+                                 const float* num_incoming, const float* ln_gamma, const float* ln_beta,
+                                 int activation, int aggregation, int normalize, int num_timesteps, float* out,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "gnn_film"));
+  RGNN_PROPAGATE(check_act(activation, "gnn_film"));
+  RGNN_PROPAGATE(check_agg(aggregation, "gnn_film"));
+  RGNN_REQUIRE(edge_weights && film_weights && ln_gamma && ln_beta, "gnn_film: NULL weight pointer");
+  RGNN_REQUIRE(aligned16(ln_gamma) && aligned16(ln_beta), "gnn_film: layer-norm parameters must be 16-byte aligned");
+  RGNN_REQUIRE(!normalize || num_incoming != nullptr, "gnn_film: normalize_by_num_incoming needs type_to_num_incoming_edges");
+  const int V = plan->V, L = plan->L, D = d_out;
+  for (int l = 0; l < L; ++l) RGNN_REQUIRE(edge_weights[l] && film_weights[l], "gnn_film: weight %d is NULL", l);
+  Arena ar(workspace, workspace_bytes);
+  float* T = ar.floats((size_t)V * L * D);
+  float* FW = ar.floats((size_t)V * L * 2 * D);
+  float* buf[2] = {nullptr, nullptr};
+  if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * D); buf[1] = ar.floats((size_t)V * D); }
+  RGNN_PROPAGATE(check_ws(ar, "gnn_film"));
+
+  const float* cur = h;
+  int din = d_in;
+  for (int t = 0; t < num_timesteps; ++t) {                                   // gnn_film.py:85
+    float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
+    RGNN_PROPAGATE(gemm_shared_a(cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));        // :94 on nodes
+    RGNN_PROPAGATE(gemm_shared_a(cur, V, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));  // :102
+    SegParams s;
+    seg_from_plan(s, plan);
+    s.D = D; s.table = T; s.stride_idx = (long)L * D; s.stride_type = D;
+    s.num_incoming = normalize ? num_incoming : nullptr;                      // :96-100
+    s.msg_mode = MSG_FILM; s.mod_table = FW; s.mod_stride_node = (long)L * 2 * D; s.mod_stride_type = 2 * D;   // :103-108
+    s.act_msg = activation;                                                   // :112 (before the sum)
+    s.agg = aggregation;                                                      // :113-116
+    s.ln_gamma = ln_gamma + (size_t)t * D; s.ln_beta = ln_beta + (size_t)t * D;   // :120
+    s.out = dst; s.ld_out = D;
+    RGNN_PROPAGATE(launch_seg_reduce(s, stream));
+    cur = dst; din = D;
+  }
+  return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gnns/gnn_edge_mlp.py:7-122
+// ---------------------------------------------------------------------------------------------
+extern "C" int rgnn_edge_mlp_forward(const rgnn_plan_t* plan, const float* h, int32_t d_in, int32_t d_out,
+                                     const float* const* mlp_kernels, const int32_t* mlp_dims,
+                                     int num_edge_hidden_layers, const float* num_incoming, const float* ln_gamma,
+                                     const float* ln_beta, int activation, int aggregation, int normalize,
+                                     int use_target, int num_timesteps, float* out, void* workspace,
+                                     size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "gnn_edge_mlp"));
+  RGNN_PROPAGATE(check_act(activation, "gnn_edge_mlp"));
+  RGNN_PROPAGATE(check_agg(aggregation, "gnn_edge_mlp"));
+  RGNN_REQUIRE(mlp_kernels && mlp_dims && ln_gamma && ln_beta, "gnn_edge_mlp: NULL weight pointer");
+  RGNN_REQUIRE(num_edge_hidden_layers >= 0, "gnn_edge_mlp: num_edge_hidden_layers %d < 0", num_edge_hidden_layers);
+  RGNN_REQUIRE(!normalize || num_incoming != nullptr, "gnn_edge_mlp: normalize_by_num_incoming needs type_to_num_incoming_edges");
+  const int nl = num_edge_hidden_layers + 1;
+  RGNN_REQUIRE(nl <= RGNN_MAX_MLP_LAYERS && mlp_dims[nl] == d_out, "gnn_edge_mlp: MLP output dim %d != state_dim %d", mlp_dims[nl <= RGNN_MAX_MLP_LAYERS ? nl : 0], d_out);
+  const int V = plan->V, D = d_out;
+  Arena ar(workspace, workspace_bytes);
+  float* buf[2] = {nullptr, nullptr};
+  if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * D); buf[1] = ar.floats((size_t)V * D); }
+  const size_t mark = ar.used;
+  const float* cur = h;
+  for (int t = 0; t < num_timesteps; ++t) {                                   // gnn_edge_mlp.py:84
+    float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
+    ar.used = mark;                                                           // scratch of the previous timestep is dead
+    MsgSource ms;
+    RGNN_PROPAGATE(build_mlp_messages(plan, cur, d_in, mlp_kernels, mlp_dims, nl, use_target, RGNN_ACT_ELU, ar, stream, &ms));  // :76,:102
+    RGNN_PROPAGATE(check_ws(ar, "gnn_edge_mlp"));
+    SegParams s;
+    seg_from_plan(s, plan);
+    seg_from_source(s, ms);
+    s.num_incoming = normalize ? num_incoming : nullptr;                      // :104-108
+    s.act_msg = activation;                                                   // :112
+    s.agg = aggregation;                                                      // :113-116
+    s.ln_gamma = ln_gamma + (size_t)t * D; s.ln_beta = ln_beta + (size_t)t * D;   // :119
+    s.out = dst; s.ld_out = D;
+    RGNN_PROPAGATE(launch_seg_reduce(s, stream));
+    cur = dst;
+  }
+  return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gnns/rgin.py:7-142
+// ---------------------------------------------------------------------------------------------
+extern "C" int rgnn_rgin_forward(const rgnn_plan_t* plan, const float* h, int32_t d_in, int32_t d_out,
+                                 const float* const* edge_mlp_kernels, const int32_t* edge_mlp_dims,
+                                 int num_edge_mlp_hidden_layers, const float* const* aggr_kernels,
+                                 const int32_t* aggr_dims, int num_aggr_mlp_hidden_layers, const float* ln_gamma,
+                                 const float* ln_beta, int activation, int aggregation, int use_target,
+                                 int num_timesteps, float* out, void* workspace, size_t workspace_bytes,
+                                 void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "rgin"));
+  RGNN_PROPAGATE(check_act(activation, "rgin"));
+  RGNN_PROPAGATE(check_agg(aggregation, "rgin"));
+  RGNN_REQUIRE(ln_gamma && ln_beta, "rgin: NULL layer-norm parameters");
+  const int nl_edge = num_edge_mlp_hidden_layers < 0 ? 0 : num_edge_mlp_hidden_layers + 1;
+  const int nl_aggr = num_aggr_mlp_hidden_layers < 0 ? 0 : num_aggr_mlp_hidden_layers + 1;
+  RGNN_REQUIRE(nl_edge == 0 || (edge_mlp_kernels && edge_mlp_dims), "rgin: NULL edge MLP table");
+  RGNN_REQUIRE(nl_aggr == 0 || (aggr_kernels && aggr_dims), "rgin: NULL aggregation MLP table");
+  RGNN_REQUIRE(nl_aggr <= RGNN_MAX_MLP_LAYERS, "rgin: aggregation MLP too deep");
+  const int V = plan->V, D = d_out;
+  Arena ar(workspace, workspace_bytes);
+  float* buf[2] = {nullptr, nullptr};
+  if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * D); buf[1] = ar.floats((size_t)V * D); }
+  const size_t mark = ar.used;
+  const float* cur = h;
+  for (int t = 0; t < num_timesteps; ++t) {                                   // rgin.py:103
+    float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
+    ar.used = mark;
+    MsgSource ms;
+    RGNN_PROPAGATE(build_mlp_messages(plan, cur, d_in, edge_mlp_kernels, edge_mlp_dims, nl_edge, use_target, activation, ar, stream, &ms));  // :95,:122
+    RGNN_PROPAGATE(check_ws(ar, "rgin"));
+    const int width = ms.width;
+    SegParams s;
+    seg_from_plan(s, plan);
+    seg_from_source(s, ms);
+    s.act_msg = (nl_edge > 0) ? activation : RGNN_ACT_LINEAR;                 // :128-129
+    s.agg = aggregation;                                                      // :130-133
+    if (nl_aggr == 0) {
+      RGNN_REQUIRE(width == D, "rgin: message width %d != state_dim %d and no aggregation MLP maps it", width, D);
+      s.act_out = activation;                                                 // :138
+      s.ln_gamma = ln_gamma + (size_t)t * D; s.ln_beta = ln_beta + (size_t)t * D;   // :139
+      s.out = dst; s.ld_out = D;
+      RGNN_PROPAGATE(launch_seg_reduce(s, stream));
+    } else {
+      RGNN_REQUIRE(aggr_dims[0] == width && aggr_dims[nl_aggr] == D, "rgin: aggregation MLP dims [%d .. %d] do not match [%d .. %d]",
+                   aggr_dims[0], aggr_dims[nl_aggr], width, D);
+      float* agg = ar.floats((size_t)V * width);
+      RGNN_PROPAGATE(check_ws(ar, "rgin"));
+      s.out = agg; s.ld_out = width;
+      RGNN_PROPAGATE(launch_seg_reduce(s, stream));
+      const float* prev = agg;
+      for (int j = 0; j < nl_aggr; ++j) {                                     // :136-137 (+ :138 fused into the last layer)
+        RGNN_REQUIRE(aggr_kernels[j] != nullptr && (aggr_dims[j + 1] % 4) == 0, "rgin: aggregation MLP layer %d invalid", j);
+        float* next = ar.floats((size_t)V * aggr_dims[j + 1]);
+        RGNN_PROPAGATE(check_ws(ar, "rgin"));
+        GemmParams g;
+        g.A1 = prev; g.lda1 = aggr_dims[j]; g.K1 = aggr_dims[j];
+        g.B1 = aggr_kernels[j]; g.ldb1 = aggr_dims[j + 1];
+        g.M = V; g.N = aggr_dims[j + 1]; g.C = next; g.ldc = aggr_dims[j + 1];
+        g.act = activation;   // hidden layers: MLP activation (rgin.py:80); last layer: the explicit activation of :138
+        RGNN_PROPAGATE(launch_gemm(g, stream));
+        prev = next;
+      }
+      RGNN_PROPAGATE(launch_layer_norm(prev, V, D, ln_gamma + (size_t)t * D, ln_beta + (size_t)t * D, dst, stream));  // :139
+    }
+    cur = dst;
+  }
+  return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// building blocks
+// ---------------------------------------------------------------------------------------------
+extern "C" int rgnn_segment_aggregate(const rgnn_plan_t* plan, const float* data, int32_t d, int aggregation,
+                                      float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_REQUIRE(plan != nullptr && data != nullptr && out != nullptr, "segment_aggregate: NULL argument");
+  RGNN_PROPAGATE(check_agg(aggregation, "segment_aggregate"));
+  SegParams s;
+  seg_from_plan(s, plan);
+  s.e_idx = plan->e_orig; s.table = data; s.stride_idx = d; s.stride_type = 0; s.D = d;
+  s.agg = aggregation; s.out = out; s.ld_out = d;
+  return launch_seg_reduce(s, stream);
+}
+
+extern "C" int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const float* b, int32_t n, const float* bias,
+                                  int activation, float* c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_REQUIRE(a && b && c, "dense: NULL argument");
+  RGNN_PROPAGATE(check_act(activation, "dense"));
+  GemmParams g;
+  g.A1 = a; g.lda1 = k; g.K1 = k; g.B1 = b; g.ldb1 = n; g.M = m; g.N = n; g.C = c; g.ldc = n;
+  g.bias = bias; g.act = activation;
+  return launch_gemm(g, stream);
+}
+
+extern "C" int rgnn_layer_norm(const float* x, int32_t rows, int32_t d, const float* gamma, const float* beta,
+                               float* out, void* stream_) {
+  RGNN_REQUIRE(x && gamma && beta && out, "layer_norm: NULL argument");
+  return launch_layer_norm(x, rows, d, gamma, beta, out, static_cast<cudaStream_t>(stream_));
+}

@@ -1,0 +1,22 @@
+// plan.cuh -- device-resident graph structure of one batch (see rgnn_plan_create in include/rgnn.h).
+#pragma once
+#include "common.cuh"
+
+struct rgnn_plan {
+  int32_t V = 0;
+  int32_t L = 0;
+  int64_t M = 0;
+  // CSR by target over all edge types; incoming edges of v sorted by (type, original position)
+  int32_t* seg_off = nullptr;   // [V+1]
+  int32_t* e_src = nullptr;     // [M]
+  int32_t* e_type = nullptr;    // [M]
+  int32_t* e_orig = nullptr;    // [M] position in the type-major concatenation of the inputs
+  // the inputs, concatenated type-major (rows of per-edge matrices live in this order)
+  int32_t* o_src = nullptr;     // [M]
+  int32_t* o_tgt = nullptr;     // [M]
+  int32_t type_off[RGNN_MAX_EDGE_TYPES + 1] = {0};   // host copy: block of type l = [type_off[l], type_off[l+1])
+  int32_t max_type_edges = 0;
+  int device = 0;
+  void* block = nullptr;        // the one pool allocation behind all arrays above
+  cudaStream_t stream = nullptr; // creation stream (the block is freed stream-ordered on it)
+};

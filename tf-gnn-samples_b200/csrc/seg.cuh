@@ -1,0 +1,72 @@
+// seg.cuh -- edge-stage kernels: gather message rows by source, modulate, segment-reduce to the target.
+#pragma once
+#include "common.cuh"
+#include "plan.cuh"
+
+namespace rgnn {
+
+enum MsgMode {
+  MSG_LINEAR = 0,   // m = s * t                      (RGCN / GGNN / RGIN / materialised per-edge MLP outputs)
+  MSG_FILM = 1,     // m = gamma * (s * t) + beta     (gnn_film.py:96-108)
+  MSG_ADDTGT = 2,   // m = s * (t + q)                ([h_u | h_v] . W  ==  h_u.W_src + h_v.W_tgt : rgcn.py:91-96, gnn_edge_mlp.py:95-102)
+};
+
+struct SegParams {
+  int V = 0, L = 1, D = 0;
+  const int32_t* seg_off = nullptr;
+  const int32_t* e_idx = nullptr;      // plan->e_src (tables indexed by node) or plan->e_orig (per-edge matrices)
+  const int32_t* e_type = nullptr;
+  const float* table = nullptr;        // message row of edge e = table + e_idx[e]*stride_idx + e_type[e]*stride_type
+  long stride_idx = 0, stride_type = 0;
+  const float* num_incoming = nullptr; // [L, V] fp32 -> s = 1/(c + 1e-7) (rgcn.py:100-104); NULL -> s = 1
+  int msg_mode = MSG_LINEAR;
+  const float* mod_table = nullptr;    // FILM: gamma at +0, beta at +D ; ADDTGT: q.  row = mod_table + v*mod_stride_node + type*mod_stride_type
+  long mod_stride_node = 0, mod_stride_type = 0;
+  int act_msg = RGNN_ACT_LINEAR;       // activation applied per message before the reduction
+  int agg = RGNN_AGG_SUM;
+  int act_out = RGNN_ACT_LINEAR;       // activation applied to the aggregate
+  const float* ln_gamma = nullptr;     // non-NULL -> tf.contrib.layers.layer_norm epilogue (eps 1e-12)
+  const float* ln_beta = nullptr;
+  float* out = nullptr;
+  int ld_out = 0;
+};
+int launch_seg_reduce(const SegParams& p, cudaStream_t stream);
+
+struct RgatParams {
+  int V = 0, L = 1, D = 0, K = 1;
+  const int32_t* seg_off = nullptr;
+  const int32_t* e_src = nullptr;
+  const int32_t* e_type = nullptr;
+  const float* table = nullptr;        // T [V, L, D]
+  const float* s_src = nullptr;        // [V, L, K]
+  const float* s_tgt = nullptr;        // [V, L, K]
+  int act_out = RGNN_ACT_LINEAR;
+  float* out = nullptr;
+};
+int launch_seg_rgat(const RgatParams& p, cudaStream_t stream);
+
+struct AttnTable { const float* att[RGNN_MAX_EDGE_TYPES]; };
+// s_src[n,l,k] = <att_l[k*2d : k*2d+d], T[n,l,k*d:(k+1)*d]>, s_tgt with att_l[k*2d+d : (k+1)*2d]  (rgat.py:106-115)
+int launch_rgat_scores(const float* table, int V, int L, int D, int K, const AttnTable& att, float* s_src,
+                       float* s_tgt, cudaStream_t stream);
+
+// X[i, :] (i in type-major original order) = act(P[src_i, type, :] + Q[tgt_i, type, :])   (pq != NULL), or
+// X[i, :] = [h[src_i] | h[tgt_i]]                                                         (concat mode)
+struct EdgeBuildParams {
+  int L = 1, D = 0;                     // D = width of P / Q rows (or of h in concat mode)
+  const int32_t* o_src = nullptr;
+  const int32_t* o_tgt = nullptr;
+  int32_t type_off[RGNN_MAX_EDGE_TYPES + 1];
+  int max_type_edges = 0;
+  const float* p = nullptr; long p_stride_node = 0, p_stride_type = 0;
+  const float* q = nullptr; long q_stride_node = 0, q_stride_type = 0;   // NULL -> concat mode
+  int concat = 0;
+  int act = RGNN_ACT_LINEAR;
+  float* x = nullptr; int ldx = 0;
+};
+int launch_edge_build(const EdgeBuildParams& p, cudaStream_t stream);
+
+int launch_layer_norm(const float* x, int rows, int D, const float* gamma, const float* beta, float* out,
+                      cudaStream_t stream);
+
+}  // namespace rgnn

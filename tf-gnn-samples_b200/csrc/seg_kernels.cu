@@ -1,0 +1,396 @@
+// seg_kernels.cu -- the edge stage of every layer as fused sorted-segment kernels.
+//
+// One warp owns one target node.  Its incoming edges are contiguous in the plan (CSR by target,
+// all edge types), so the warp streams the gathered message rows T[src, type, :] with 128-bit
+// coalesced loads (one row = D*4 bytes, each lane reads NV float4), applies the per-message
+// scale 1/(c+1e-7) / FiLM modulation / activation in registers, reduces in registers, applies
+// the layer's epilogue (aggregation divisor, activation, layer norm) and writes the output row
+// once.  No [M, D] message matrix, no concat, no atomics, deterministic order.
+//
+// Replaces: tf.nn.embedding_lookup + scale + tf.concat + tf.unsorted_segment_* + activation
+// (gnns/rgcn.py:84-114, ggnn.py:76-90, gnn_film.py:88-120, gnn_edge_mlp.py:87-119,
+// rgin.py:106-139), dpu_utils unsorted_segment_log_softmax + per-head weighted segment sums
+// (rgat.py:120-138), tf.contrib.layers.layer_norm (A.5).
+#include "seg.cuh"
+
+namespace rgnn {
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int UNROLL = 4;     // message rows in flight per warp
+
+__device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+__device__ __forceinline__ float4 mul4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {   // a*b + c
+  return make_float4(a.x * b.x + c.x, a.y * b.y + c.y, a.z * b.z + c.z, a.w * b.w + c.w);
+}
+
+// tf.contrib.layers.layer_norm over one row held by a warp (A.5): biased variance, eps 1e-12,
+// evaluated as x*inv + (beta - mean*inv) with inv = rsqrt(var + eps) * gamma.
+template <int NV>
+__device__ __forceinline__ void warp_layer_norm(float4 (&x)[NV], const bool (&ok)[NV], int D, int lane,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta) {
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (ok[k]) s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (ok[k]) {
+      const float a = x[k].x - mean, b = x[k].y - mean, c = x[k].z - mean, d = x[k].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  const float var = warp_sum(q) / (float)D;
+  const float rstd = 1.0f / sqrtf(var + 1e-12f);
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (ok[k]) {
+      const int col = k * 128 + lane * 4;
+      const float4 g = ldg4(gamma + col), b = ldg4(beta + col);
+      float inv;
+      inv = rstd * g.x; x[k].x = x[k].x * inv + (b.x - mean * inv);
+      inv = rstd * g.y; x[k].y = x[k].y * inv + (b.y - mean * inv);
+      inv = rstd * g.z; x[k].z = x[k].z * inv + (b.z - mean * inv);
+      inv = rstd * g.w; x[k].w = x[k].w * inv + (b.w - mean * inv);
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const __grid_constant__ SegParams p) {
+  const int lane = threadIdx.x & 31;
+  const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (v >= p.V) return;
+  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+
+  bool ok[NV];
+  float4 acc[NV];
+  const float init = (p.agg == RGNN_AGG_MAX) ? -FLT_MAX : 0.0f;   // empty max segment -> lowest() (A.2)
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ok[k] = (k * 128 + lane * 4) < p.D;
+    acc[k] = f4(init);
+  }
+
+  int cur_type = -1;
+  float4 m0[NV], m1[NV];   // gamma/beta (FILM) or q (ADDTGT) of the current (v, type) run
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { m0[k] = f4(1.0f); m1[k] = f4(0.0f); }
+
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int n = min(32, end - e0);
+    int my_idx = 0, my_type = 0;
+    float my_scale = 1.0f;
+    if (lane < n) {
+      my_idx = __ldg(p.e_idx + e0 + lane);
+      my_type = __ldg(p.e_type + e0 + lane);
+      if (p.num_incoming != nullptr)   // 1.0f / (c + SMALL_NUMBER) evaluated in fp32 like the reference
+        my_scale = 1.0f / (__ldg(p.num_incoming + (size_t)my_type * p.V + v) + 1e-7f);
+    }
+    for (int j = 0; j < n; j += UNROLL) {
+      float4 r[UNROLL][NV];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (j + u < n) {
+          const int idx = __shfl_sync(0xffffffffu, my_idx, j + u);
+          const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
+          const float* row = p.table + (size_t)idx * p.stride_idx + (size_t)ty * p.stride_type + lane * 4;
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (ok[k]) r[u][k] = ldg4(row + k * 128);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (j + u < n) {
+          const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
+          const float sc = __shfl_sync(0xffffffffu, my_scale, j + u);
+          if (p.msg_mode != MSG_LINEAR && ty != cur_type) {   // warp-uniform: new (v, type) run
+            cur_type = ty;
+            const float* mrow = p.mod_table + (size_t)v * p.mod_stride_node + (size_t)ty * p.mod_stride_type + lane * 4;
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+              if (ok[k]) {
+                m0[k] = ldg4(mrow + k * 128);
+                if (p.msg_mode == MSG_FILM) m1[k] = ldg4(mrow + p.D + k * 128);
+              }
+          }
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (ok[k]) {
+              float4 m = r[u][k];
+              if (p.msg_mode == MSG_LINEAR) {
+                if (p.num_incoming != nullptr) m = mul4(m, sc);
+              } else if (p.msg_mode == MSG_FILM) {
+                if (p.num_incoming != nullptr) m = mul4(m, sc);
+                m = fma4(m0[k], m, m1[k]);
+              } else {
+                m = add4(m, m0[k]);
+                if (p.num_incoming != nullptr) m = mul4(m, sc);
+              }
+              m = act4(m, p.act_msg);
+              acc[k] = (p.agg == RGNN_AGG_MAX) ? max4(acc[k], m) : add4(acc[k], m);
+            }
+        }
+      }
+    }
+  }
+
+  // aggregation divisor (A.2): mean = sum / max(n,1); sqrt_n = sum / sqrt(max(n,1))
+  if (p.agg == RGNN_AGG_MEAN || p.agg == RGNN_AGG_SQRT_N) {
+    const float cnt = fmaxf((float)(end - beg), 1.0f);
+    const float div = (p.agg == RGNN_AGG_MEAN) ? cnt : sqrtf(cnt);
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      acc[k] = make_float4(acc[k].x / div, acc[k].y / div, acc[k].z / div, acc[k].w / div);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = act4(acc[k], p.act_out);
+  if (p.ln_gamma != nullptr) warp_layer_norm<NV>(acc, ok, p.D, lane, p.ln_gamma, p.ln_beta);
+  float* orow = p.out + (size_t)v * p.ld_out + lane * 4;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (ok[k]) *reinterpret_cast<float4*>(orow + k * 128) = acc[k];
+}
+
+// ---- RGAT: per-target, per-head online softmax fused with the weighted sum -----------------
+template <int NV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __grid_constant__ RgatParams p) {
+  const int lane = threadIdx.x & 31;
+  const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (v >= p.V) return;
+  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  const int dh = p.D / p.K;   // per-head width, multiple of 4 (checked on the host)
+
+  bool ok[NV];
+  int head[NV];
+  float4 acc[NV];
+  float mx[NV], den[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int col = k * 128 + lane * 4;
+    ok[k] = col < p.D;
+    head[k] = ok[k] ? col / dh : 0;
+    acc[k] = f4(0.0f);
+    mx[k] = -INFINITY;
+    den[k] = 0.0f;
+  }
+  const size_t LK = (size_t)p.L * p.K;
+
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int n = min(32, end - e0);
+    int my_src = 0, my_type = 0;
+    if (lane < n) {
+      my_src = __ldg(p.e_src + e0 + lane);
+      my_type = __ldg(p.e_type + e0 + lane);
+    }
+    for (int j = 0; j < n; j += UNROLL) {
+      float4 r[UNROLL][NV];
+      float lg[UNROLL][NV];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (j + u < n) {
+          const int src = __shfl_sync(0xffffffffu, my_src, j + u);
+          const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
+          const float* row = p.table + ((size_t)src * p.L + ty) * p.D + lane * 4;
+          const float* ss = p.s_src + (size_t)src * LK + (size_t)ty * p.K;
+          const float* st = p.s_tgt + (size_t)v * LK + (size_t)ty * p.K;
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (ok[k]) {
+              r[u][k] = ldg4(row + k * 128);
+              lg[u][k] = __ldg(ss + head[k]) + __ldg(st + head[k]);
+            }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (j + u < n) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (ok[k]) {
+              float x = lg[u][k];
+              x = x > 0.0f ? x : 0.2f * x;                   // tf.nn.leaky_relu (rgat.py:113)
+              const float mnew = fmaxf(mx[k], x);
+              const float corr = expf(mx[k] - mnew);          // exp(-inf) = 0 on the first message
+              const float w = expf(x - mnew);
+              den[k] = den[k] * corr + w;
+              acc[k].x = acc[k].x * corr + w * r[u][k].x;
+              acc[k].y = acc[k].y * corr + w * r[u][k].y;
+              acc[k].z = acc[k].z * corr + w * r[u][k].z;
+              acc[k].w = acc[k].w * corr + w * r[u][k].w;
+              mx[k] = mnew;
+            }
+        }
+      }
+    }
+  }
+  float* orow = p.out + (size_t)v * p.D + lane * 4;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (ok[k]) {
+      float4 o = f4(0.0f);                                    // no incoming message -> zeros (A.7)
+      if (end > beg) o = make_float4(acc[k].x / den[k], acc[k].y / den[k], acc[k].z / den[k], acc[k].w / den[k]);
+      *reinterpret_cast<float4*>(orow + k * 128) = act4(o, p.act_out);
+    }
+}
+
+// one thread per (node, type, head)
+__global__ void rgat_scores_kernel(const float* __restrict__ table, int V, int L, int D, int K,
+                                   const __grid_constant__ AttnTable att, float* __restrict__ s_src,
+                                   float* __restrict__ s_tgt) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)V * L * K;
+  if (i >= total) return;
+  const int k = (int)(i % K);
+  const int l = (int)((i / K) % L);
+  const int dh = D / K;
+  const float* row = table + (i / K) * (long)D + (long)k * dh;      // T[n, l, k*dh : (k+1)*dh]
+  const float* a = att.att[l] + (long)k * 2 * dh;                    // [src part | tgt part] (rgat.py:110-111)
+  float ss = 0.0f, st = 0.0f;
+  for (int c = 0; c < dh; c += 4) {
+    const float4 t = ldg4(row + c);
+    const float4 as = ldg4(a + c), at = ldg4(a + dh + c);
+    ss += t.x * as.x + t.y * as.y + t.z * as.z + t.w * as.w;
+    st += t.x * at.x + t.y * at.y + t.z * at.z + t.w * at.w;
+  }
+  s_src[i] = ss;
+  s_tgt[i] = st;
+}
+
+// grid = (ceil(max_type_edges / WARPS), L); one warp per edge row
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) edge_build_kernel(const __grid_constant__ EdgeBuildParams p) {
+  const int lane = threadIdx.x & 31;
+  const int l = blockIdx.y;
+  const int i = p.type_off[l] + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (i >= p.type_off[l + 1]) return;
+  const int src = __ldg(p.o_src + i), tgt = __ldg(p.o_tgt + i);
+  float* xrow = p.x + (size_t)i * p.ldx;
+  const float* prow = p.p + (size_t)src * p.p_stride_node + (size_t)l * p.p_stride_type;
+  if (p.concat) {
+    const float* qrow = p.p + (size_t)tgt * p.p_stride_node;
+    for (int c = lane * 4; c < p.D; c += 128) {
+      *reinterpret_cast<float4*>(xrow + c) = ldg4(prow + c);
+      *reinterpret_cast<float4*>(xrow + p.D + c) = ldg4(qrow + c);
+    }
+  } else {
+    const float* qrow = p.q + (size_t)tgt * p.q_stride_node + (size_t)l * p.q_stride_type;
+    for (int c = lane * 4; c < p.D; c += 128)
+      *reinterpret_cast<float4*>(xrow + c) = act4(add4(ldg4(prow + c), ldg4(qrow + c)), p.act);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) layer_norm_kernel(const float* __restrict__ x, int rows, int D,
+                                                                          const float* __restrict__ gamma,
+                                                                          const float* __restrict__ beta,
+                                                                          float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  bool ok[NV];
+  float4 v[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ok[k] = (k * 128 + lane * 4) < D;
+    v[k] = ok[k] ? ldg4(x + (size_t)r * D + k * 128 + lane * 4) : f4(0.0f);
+  }
+  warp_layer_norm<NV>(v, ok, D, lane, gamma, beta);
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (ok[k]) *reinterpret_cast<float4*>(out + (size_t)r * D + k * 128 + lane * 4) = v[k];
+}
+
+inline int nv_for(int D) { return (D + 127) / 128; }
+
+}  // namespace
+
+int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
+  RGNN_REQUIRE(p.D > 0 && (p.D % 4) == 0, "segment reduce: state dim %d must be a positive multiple of 4", p.D);
+  if (p.D > RGNN_MAX_STATE_DIM) {
+    set_error("segment reduce: state dim %d > %d not supported by this build", p.D, RGNN_MAX_STATE_DIM);
+    return RGNN_E_UNSUPPORTED;
+  }
+  RGNN_REQUIRE(p.agg >= RGNN_AGG_SUM && p.agg <= RGNN_AGG_SQRT_N, "Unknown aggregation function code %d", p.agg);
+  RGNN_REQUIRE((p.stride_idx % 4) == 0 && (p.stride_type % 4) == 0 && (p.ld_out % 4) == 0 && aligned16(p.table) && aligned16(p.out),
+               "segment reduce: rows must be 16-byte aligned");
+  if (p.V == 0) return RGNN_OK;
+  const dim3 grid((p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  switch (nv_for(p.D)) {
+    case 1: seg_reduce_kernel<1><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    case 2: seg_reduce_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    case 3: seg_reduce_kernel<3><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    default: seg_reduce_kernel<4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+  }
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+int launch_seg_rgat(const RgatParams& p, cudaStream_t stream) {
+  RGNN_REQUIRE(p.D > 0 && (p.D % 4) == 0 && p.K >= 1 && (p.D % p.K) == 0, "rgat: state dim %d / heads %d invalid", p.D, p.K);
+  if (p.D > RGNN_MAX_STATE_DIM || ((p.D / p.K) % 4) != 0) {
+    set_error("rgat: state dim %d (max %d) with per-head dim %d (must be a multiple of 4) not supported", p.D,
+              RGNN_MAX_STATE_DIM, p.D / p.K);
+    return RGNN_E_UNSUPPORTED;
+  }
+  if (p.V == 0) return RGNN_OK;
+  const dim3 grid((p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  switch (nv_for(p.D)) {
+    case 1: seg_rgat_kernel<1><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    case 2: seg_rgat_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    case 3: seg_rgat_kernel<3><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    default: seg_rgat_kernel<4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+  }
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+int launch_rgat_scores(const float* table, int V, int L, int D, int K, const AttnTable& att, float* s_src,
+                       float* s_tgt, cudaStream_t stream) {
+  const long total = (long)V * L * K;
+  if (total == 0) return RGNN_OK;
+  rgat_scores_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(table, V, L, D, K, att, s_src, s_tgt);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+int launch_edge_build(const EdgeBuildParams& p, cudaStream_t stream) {
+  RGNN_REQUIRE(p.D > 0 && (p.D % 4) == 0, "edge build: width %d must be a positive multiple of 4", p.D);
+  if (p.max_type_edges == 0) return RGNN_OK;
+  const dim3 grid((p.max_type_edges + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, p.L);
+  edge_build_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+int launch_layer_norm(const float* x, int rows, int D, const float* gamma, const float* beta, float* out,
+                      cudaStream_t stream) {
+  RGNN_REQUIRE(D > 0 && (D % 4) == 0, "layer norm: dim %d must be a positive multiple of 4", D);
+  if (D > RGNN_MAX_STATE_DIM) {
+    set_error("layer norm: dim %d > %d not supported by this build", D, RGNN_MAX_STATE_DIM);
+    return RGNN_E_UNSUPPORTED;
+  }
+  if (rows == 0) return RGNN_OK;
+  const dim3 grid((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  switch (nv_for(D)) {
+    case 1: layer_norm_kernel<1><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(x, rows, D, gamma, beta, out); break;
+    case 2: layer_norm_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(x, rows, D, gamma, beta, out); break;
+    case 3: layer_norm_kernel<3><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(x, rows, D, gamma, beta, out); break;
+    default: layer_norm_kernel<4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(x, rows, D, gamma, beta, out); break;
+  }
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+}  // namespace rgnn

@@ -1,0 +1,245 @@
+"""ctypes binding of librgnn.so (include/rgnn.h) + the per-batch GraphPlan.
+
+This is the thin host layer the north star asks for: Python -> ctypes -> C ABI -> CUDA.  torch is
+used for device memory (``Tensor.data_ptr()``) and the stream (``torch.cuda.current_stream()``).
+There is no CPU path: if the library cannot be loaded the first call raises RgnnError.
+"""
+import ctypes
+import os
+import threading
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _build
+
+c_void_p, c_int, c_int32, c_int64, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+c_char_p = ctypes.c_char_p
+
+RGNN_OK, RGNN_E_INVALID, RGNN_E_CUDA, RGNN_E_WORKSPACE, RGNN_E_UNSUPPORTED = 0, -1, -2, -3, -4
+
+
+class RgnnError(RuntimeError):
+    """Raised when a librgnn call returns a negative status (message from rgnn_last_error())."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__("librgnn error %d: %s" % (code, message))
+        self.code = code
+        self.message = message
+
+
+# every exported symbol of include/rgnn.h: name -> (restype, argtypes)
+_PTR = c_void_p
+SIGNATURES = {
+    "rgnn_version": (c_int, []),
+    "rgnn_last_error": (c_char_p, []),
+    "rgnn_launch_count": (c_int64, []),
+    "rgnn_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int32, c_int32, _PTR, _PTR, _PTR]),
+    "rgnn_plan_destroy": (c_int, [_PTR]),
+    "rgnn_plan_num_nodes": (c_int32, [_PTR]),
+    "rgnn_plan_num_edge_types": (c_int32, [_PTR]),
+    "rgnn_plan_num_edges": (c_int64, [_PTR]),
+    "rgnn_plan_export": (c_int, [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "rgnn_workspace_bytes": (c_size_t, [_PTR, c_int, c_int32, c_int32, c_int32]),
+    "rgnn_rgcn_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int, c_int, c_int,
+                                  _PTR, _PTR, c_size_t, _PTR]),
+    "rgnn_ggnn_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, _PTR, _PTR, c_int, c_int, c_int, c_int,
+                                  _PTR, _PTR, c_size_t, _PTR]),
+    "rgnn_rgat_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int,
+                                  _PTR, _PTR, c_size_t, _PTR]),
+    "rgnn_film_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, _PTR, _PTR, _PTR, c_int, c_int, c_int, c_int,
+                                  _PTR, _PTR, c_size_t, _PTR]),
+    "rgnn_edge_mlp_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, _PTR, _PTR, _PTR,
+                                      c_int, c_int, c_int, c_int, c_int, _PTR, _PTR, c_size_t, _PTR]),
+    "rgnn_rgin_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, _PTR, _PTR, c_int, _PTR, _PTR,
+                                  c_int, c_int, c_int, c_int, _PTR, _PTR, c_size_t, _PTR]),
+    "rgnn_segment_aggregate": (c_int, [_PTR, _PTR, c_int32, c_int, _PTR, _PTR]),
+    "rgnn_dense_forward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
+    "rgnn_layer_norm": (c_int, [_PTR, c_int32, c_int32, _PTR, _PTR, _PTR, _PTR]),
+    "rgnn_rgcn_stack_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, c_int, _PTR, _PTR, c_int, c_int, c_int,
+                                        _PTR, _PTR, c_size_t, _PTR]),
+}
+OPTIONAL_SYMBOLS = {"rgnn_rgcn_stack_forward"}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen lib/librgnn.so and bind every symbol.  Fails loudly (RgnnError) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise RgnnError(RGNN_E_INVALID, "librgnn.so not found at %s" % path)
+            try:
+                _build.build()
+            except Exception as exc:   # no nvcc / compile error: there is no fallback path by design
+                raise RgnnError(RGNN_E_INVALID, "librgnn.so is missing and could not be built: %s" % exc)
+        lib = ctypes.CDLL(path)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                if name in OPTIONAL_SYMBOLS:
+                    continue
+                raise RgnnError(RGNN_E_INVALID, "librgnn.so at %s does not export %s (stale build?)" % (path, name))
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return _lib
+
+
+def check(code: int):
+    if code != RGNN_OK:
+        msg = load_library().rgnn_last_error()
+        raise RgnnError(code, msg.decode("utf-8", "replace") if msg else "unknown error")
+
+
+def launch_count() -> int:
+    """Kernels launched by librgnn in this process so far (bench.py 'gpu_launches')."""
+    return int(load_library().rgnn_launch_count())
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %r" % (what, type(t)))
+    if not t.is_cuda:
+        raise RgnnError(RGNN_E_INVALID, "%s lives on %s: this engine has no CPU path -- move it to a CUDA device"
+                        % (what, t.device))
+
+
+def as_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    require_cuda(t, what)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def ptr_table(tensors: Sequence[torch.Tensor]):
+    """Host array of device pointers (the 'host array of L device pointers' of include/rgnn.h)."""
+    arr = (c_void_p * max(len(tensors), 1))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+_workspaces: Dict[int, torch.Tensor] = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch buffer per device (stream-ordered reuse is safe: all work is enqueued on the
+    current stream in program order)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+class GraphPlan:
+    """Device-resident structure of one batch (CSR by target over all edge types).
+
+    Built once per batch from the task batcher's output (tasks/ppi_task.py:197-256: per-type int32
+    [E, 2] adjacency lists with node ids already offset per graph) and reused by every layer and
+    timestep.  ``adjacency_lists`` may be CUDA tensors, CPU tensors or numpy arrays (host inputs are
+    copied to ``device`` like a feed_dict would).
+    """
+
+    def __init__(self, adjacency_lists: Sequence, num_nodes: int, device: Optional[torch.device] = None):
+        lib = load_library()
+        adj: List[torch.Tensor] = []
+        for a in adjacency_lists:
+            if not isinstance(a, torch.Tensor):
+                a = torch.as_tensor(a)
+            if device is None and a.is_cuda:
+                device = a.device
+            adj.append(a)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if device is None:
+            raise RgnnError(RGNN_E_INVALID, "GraphPlan needs a CUDA device: this engine has no CPU path")
+        device = torch.device(device)
+        dev_adj = []
+        for a in adj:
+            a = a.reshape(-1, 2)
+            if a.dtype != torch.int32:
+                a = a.to(torch.int32)
+            a = a.to(device, non_blocking=True).contiguous()
+            dev_adj.append(a)
+        self.device = device
+        self.adjacency_lists = dev_adj            # keep the inputs alive / available to callers
+        self.num_nodes = int(num_nodes)
+        self.num_edge_types = len(dev_adj)
+        counts = (c_int64 * max(len(dev_adj), 1))(*[int(a.shape[0]) for a in dev_adj])
+        ptrs = ptr_table(dev_adj)
+        handle = c_void_p()
+        with torch.cuda.device(device):
+            check(lib.rgnn_plan_create(ctypes.byref(handle), self.num_nodes, self.num_edge_types, ptrs, counts,
+                                       current_stream_ptr(device)))
+        self._handle = handle
+        self.num_edges = int(lib.rgnn_plan_num_edges(handle))
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            raise RgnnError(RGNN_E_INVALID, "GraphPlan used after close()")
+        return self._handle
+
+    def export(self) -> Dict[str, torch.Tensor]:
+        """Copies of the plan arrays (tests / debugging)."""
+        lib = load_library()
+        m = max(self.num_edges, 1)
+        out = {
+            "seg_off": torch.empty(self.num_nodes + 1, dtype=torch.int32, device=self.device),
+            "e_src": torch.empty(m, dtype=torch.int32, device=self.device),
+            "e_type": torch.empty(m, dtype=torch.int32, device=self.device),
+            "e_orig": torch.empty(m, dtype=torch.int32, device=self.device),
+        }
+        with torch.cuda.device(self.device):
+            check(lib.rgnn_plan_export(self.handle, out["seg_off"].data_ptr(), out["e_src"].data_ptr(),
+                                       out["e_type"].data_ptr(), out["e_orig"].data_ptr(),
+                                       current_stream_ptr(self.device)))
+        for k in ("e_src", "e_type", "e_orig"):
+            out[k] = out[k][: self.num_edges]
+        return out
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            load_library().rgnn_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def resolve_plan(node_embeddings: torch.Tensor, adjacency_lists, plan: Optional[GraphPlan]) -> GraphPlan:
+    """Layer functions accept either raw adjacency lists (reference call convention) or a GraphPlan."""
+    if plan is not None:
+        return plan
+    if isinstance(adjacency_lists, GraphPlan):
+        return adjacency_lists
+    return GraphPlan(adjacency_lists, node_embeddings.shape[0], device=node_embeddings.device)
