@@ -214,7 +214,9 @@ def unsorted_segment_log_softmax(logits, segment_ids, num_segments):
     m = unsorted_segment_max(logits, segment_ids, num_segments)
     z = logits - m[segment_ids]
     s = unsorted_segment_sum(np.exp(z), segment_ids, num_segments)
-    return z - np.log(s)[segment_ids]
+    with np.errstate(divide="ignore"):          # empty segments have s = 0; their log is never gathered
+        log_s = np.log(s)
+    return z - log_s[segment_ids]
 
 
 def _prep(node_embeddings, adjacency_lists, dtype):

@@ -1,0 +1,117 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rgnn.h declares (no compute calls
+without a GPU); host-side mirrors of utils/utils.py keep the reference's error behaviour; the batcher
+reproduces the task batcher's tensor contract."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import tf_gnn_samples_b200 as G
+from tf_gnn_samples_b200 import _build, batching, engine, utils, weights as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "rgnn.h")) as f:
+        return sorted(set(re.findall(r"RGNN_API\s+[\w\s\*]+?\b(rgnn_\w+)\s*\(", f.read())))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for name in ("rgnn_plan_create", "rgnn_rgcn_forward", "rgnn_ggnn_forward", "rgnn_rgat_forward",
+                 "rgnn_film_forward", "rgnn_edge_mlp_forward", "rgnn_rgin_forward", "rgnn_last_error"):
+        assert name in syms
+
+
+def test_library_exports_every_declared_symbol():
+    path = _build.build()                                   # nvcc cross-compiles without a GPU
+    lib = ctypes.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), "librgnn.so does not export %s" % name
+    lib.rgnn_version.restype = ctypes.c_int
+    assert lib.rgnn_version() == 100
+    # every declared symbol has a ctypes signature in the binding and vice versa
+    assert set(declared_symbols()) == set(engine.SIGNATURES) - (engine.OPTIONAL_SYMBOLS - set(declared_symbols()))
+
+
+def test_no_cpu_fallback():
+    import torch
+    h = torch.zeros(4, 8)
+    w = W.to_torch(W.rgcn_weights(1, 8, 8), "cpu")
+    with pytest.raises(engine.RgnnError, match="no CPU path"):
+        G.sparse_rgcn_layer(h, [np.zeros((0, 2), np.int32)], np.zeros((1, 4), np.float32), 8, weights=w)
+
+
+def test_utils_error_behaviour():
+    assert utils.get_activation("ReLU") == utils.ACT_RELU and utils.get_activation("TANH") == utils.ACT_TANH
+    assert utils.get_activation(None) == utils.ACT_LINEAR and utils.get_activation("linear") == utils.ACT_LINEAR
+    with pytest.raises(ValueError, match="Unknown activation function 'swish'!"):
+        utils.get_activation("swish")
+    assert utils.get_aggregation_function("sqrt_n") == utils.AGG_SQRT_N
+    assert utils.get_aggregation_function("unsorted_segment_max") == utils.AGG_MAX
+    with pytest.raises(ValueError, match="Unknown aggregation function 'SUM'!"):   # case-sensitive like utils.py:23-33
+        utils.get_aggregation_function("SUM")
+    assert utils.get_gated_unit(8, "GRU", "tanh") == (utils.CELL_GRU, utils.ACT_TANH)
+    with pytest.raises(Exception, match="Unknown RNN cell type 'foo'."):
+        utils.get_gated_unit(8, "foo", "tanh")
+    with pytest.raises(NotImplementedError):
+        utils.get_gated_unit(8, "lstm", "tanh")
+    assert utils.SMALL_NUMBER == 1e-7 and utils.BIG_NUMBER == 1e7
+
+
+def test_ppi_like_batch_contract():
+    b = batching.ppi_like_batch()
+    assert b.num_nodes == 2245 and b.num_edges == 120245 and len(b.adjacency_lists) == 3
+    fwd, loops, bkwd = b.adjacency_lists
+    assert all(a.dtype == np.int32 and a.shape[1] == 2 for a in b.adjacency_lists)
+    assert np.array_equal(fwd[:, ::-1], bkwd)                                    # ppi_task.py:144-148
+    assert np.array_equal(loops[:, 0], np.arange(2245)) and np.array_equal(loops[:, 0], loops[:, 1])   # :125-127
+    c = b.type_to_num_incoming_edges
+    assert c.dtype == np.float32 and c.shape == (3, 2245)
+    for l, a in enumerate(b.adjacency_lists):
+        assert np.array_equal(c[l], np.bincount(a[:, 1], minlength=2245))
+    assert np.all(c[1] == 1)
+
+
+def test_pack_batch_offsets_and_budget():
+    gs = [batching.make_ppi_like_graph(100 + 10 * i, 300, seed=i) for i in range(4)]
+    b = batching.pack_batch(gs)
+    assert b.num_graphs == 4 and b.num_nodes == sum(100 + 10 * i for i in range(4))
+    off = b.graph_node_offsets
+    for l in range(3):                                                           # block-diagonal: ppi_task.py:228
+        a = b.adjacency_lists[l]
+        g_src = np.searchsorted(off, a[:, 0], side="right")
+        g_tgt = np.searchsorted(off, a[:, 1], side="right")
+        assert np.array_equal(g_src, g_tgt)
+    # strict '<' packing budget of ppi_task.py:220
+    assert batching.pack_batch(gs, max_nodes_per_batch=210).num_graphs == 1      # 100 + 110 < 210 is false
+    assert batching.pack_batch(gs, max_nodes_per_batch=211).num_graphs == 2
+    assert batching.pack_batch(gs, max_nodes_per_batch=101).num_graphs == 1
+    # an edge type with no edges becomes a (0, 2) array (:246-249)
+    g = batching.GraphSample([np.zeros((0, 2), np.int32), np.array([[0, 1]], np.int32)],
+                             np.array([[0, 0], [0, 1]]), np.zeros((2, 3), np.float32))
+    assert batching.pack_batch([g]).adjacency_lists[0].shape == (0, 2)
+
+
+def test_qm9_like_shape_statistics():
+    b = batching.qm9_like_batch(500, seed=1)
+    assert len(b.adjacency_lists) == 4
+    assert 16.5 < b.num_nodes / 500 < 19.5                                        # QM9 mean 18.0 nodes/graph
+    assert 30 < b.num_edges / 500 < 45                                            # ~37 messages/graph (tied fwd/bkwd)
+    a = b.adjacency_lists[0]
+    both = set(map(tuple, a.tolist()))
+    assert all((t, s) in both for (s, t) in list(both)[:200])                     # tie_fwd_bkwd: both directions
+
+
+def test_weight_shapes():
+    w = W.ggnn_weights(4, 32)
+    assert w["cell"]["kernel"].shape == (32, 96) and w["cell"]["bias"].shape == (96,)
+    u = w["cell"]["recurrent_kernel"][:, :32]
+    np.testing.assert_allclose(u.T @ u, np.eye(32), atol=1e-5)                    # orthogonal recurrent init
+    e = W.edge_mlp_weights(2, 16, 24, num_edge_hidden_layers=2)
+    assert [k.shape for k in e["edge_mlps"][0]] == [(32, 24), (24, 24), (24, 24)]
+    r = W.rgin_weights(2, 16, 24, num_edge_MLP_hidden_layers=None, num_aggr_MLP_hidden_layers=1, use_target_state_as_input=True)
+    assert "edge_mlps" not in r and [k.shape for k in r["aggr_mlp"]] == [(32, 24), (24, 24)]

@@ -1,0 +1,153 @@
+"""CPU: pin the oracle with everything the reference offers -- the structural
+parameter count of README.md:29 -- plus hand-computable graphs and algebraic identities.  The reference has
+no golden vectors (parity unpinned), so these are the known-answer tests the oracle itself must pass."""
+import numpy as np
+import pytest
+
+from oracle import ref_layers as R
+from tf_gnn_samples_b200 import weights as W
+
+from helpers import node_states, tiny_graph
+
+
+def test_readme_parameter_count_699257():
+    """README.md:29,60: RGCN / PPI, hidden 256, 3 layers => 699,257 parameters.
+    = input projection 50x256 (bias-free, sparse_graph_model.py:165-170) + 3 layers x 3 edge types x 256x256
+    (rgcn.py:69-75) + the extra Dense after layer 0 (sparse_graph_model.py:194-200) + output 256x121 + 121
+    (ppi_task.py:176-179).  Pins L=3 edge types and bias-free square per-type kernels."""
+    L, D, layers = 3, 256, 3
+    gnn = sum(k.size for _ in range(layers) for k in W.rgcn_weights(L, D, D)["edge_weights"])
+    assert gnn == 9 * 256 * 256
+    assert 50 * 256 + gnn + 256 * 256 + (256 * 121 + 121) == 699257
+
+
+def test_rgcn_three_node_hand_computed():
+    # nodes 0,1,2 ; type 0: 0->2, 1->2 ; type 1: 2->0.  D=2, W_0 = I, W_1 = 2I, activation linear.
+    h = np.array([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]])
+    adj = [np.array([[0, 2], [1, 2]]), np.array([[2, 0]])]
+    indeg = np.array([[0, 0, 2], [1, 0, 0]], dtype=np.float64)
+    w = {"edge_weights": [np.eye(2), 2 * np.eye(2)]}
+    out = R.sparse_rgcn_layer(h, adj, indeg, 2, activation_function="linear", weights=w)
+    want = np.array([[2 * 5.0 / (1 + 1e-7), 2 * 6.0 / (1 + 1e-7)], [0.0, 0.0],
+                     [(1.0 + 3.0) / (2 + 1e-7), (2.0 + 4.0) / (2 + 1e-7)]])
+    np.testing.assert_allclose(out, want, rtol=1e-12)
+    out_nonorm = R.sparse_rgcn_layer(h, adj, indeg, 2, activation_function="linear",
+                                     normalize_by_num_incoming=False, weights=w)
+    np.testing.assert_allclose(out_nonorm, [[10.0, 12.0], [0.0, 0.0], [4.0, 6.0]], rtol=1e-12)
+
+
+def test_segment_ops_empty_segments():
+    data = np.array([[1.0, -2.0], [3.0, 4.0]])
+    ids = np.array([2, 2])
+    assert np.array_equal(R.unsorted_segment_sum(data, ids, 4), [[0, 0], [0, 0], [4, 2], [0, 0]])
+    m = R.unsorted_segment_max(data, ids, 4)
+    assert m[0, 0] == np.finfo(np.float32).min and np.array_equal(m[2], [3, 4])          # lowest() (A.2)
+    np.testing.assert_allclose(R.unsorted_segment_mean(data, ids, 4)[2], [2.0, 1.0])
+    np.testing.assert_allclose(R.unsorted_segment_sqrt_n(data, ids, 4)[2], np.array([4.0, 2.0]) / np.sqrt(2))
+    assert np.all(R.unsorted_segment_mean(data, ids, 4)[0] == 0)
+
+
+def test_activation_table():
+    x = np.array([-2.0, -0.5, 0.0, 0.5, 2.0])
+    np.testing.assert_allclose(R.get_activation("leaky_relu")(x), np.where(x > 0, x, 0.2 * x))
+    np.testing.assert_allclose(R.get_activation("ELU")(x), np.where(x > 0, x, np.exp(x) - 1))
+    np.testing.assert_allclose(R.get_activation("selu")(x)[-1], 1.0507009873554805 * 2.0)
+    from math import erf, sqrt
+    np.testing.assert_allclose(R.get_activation("gelu")(x), [v * 0.5 * (1 + erf(v / sqrt(2))) for v in x], rtol=1e-12)
+    assert R.get_activation("linear") is None and R.get_activation(None) is None
+    with pytest.raises(ValueError):
+        R.get_activation("swish")
+    with pytest.raises(ValueError):
+        R.get_aggregation_function("median")
+    with pytest.raises(Exception, match="Unknown RNN cell type"):
+        R.get_gated_unit("transformer", "tanh")
+
+
+def test_gru_cell_hand_computed():
+    # D=1: z = hs(x*wz + h*uz + bz), r = hs(...), hh = tanh(x*wh + r*h*uh + bh), h' = z*h + (1-z)*hh
+    x, h = np.array([[0.5]]), np.array([[-1.0]])
+    k, u, b = np.array([[1.0, -2.0, 0.5]]), np.array([[0.3, 0.7, -1.1]]), np.array([0.1, 0.2, -0.3])
+    hs = lambda v: min(max(0.2 * v + 0.5, 0.0), 1.0)
+    z = hs(0.5 * 1.0 + -1.0 * 0.3 + 0.1)
+    r = hs(0.5 * -2.0 + -1.0 * 0.7 + 0.2)
+    hh = np.tanh(0.5 * 0.5 + (r * -1.0) * -1.1 + -0.3)
+    want = z * -1.0 + (1 - z) * hh
+    np.testing.assert_allclose(R.gru_cell(x, h, k, u, b, np.tanh), [[want]], rtol=1e-12)
+
+
+def test_layer_norm_eps_and_affine():
+    x = np.array([[1.0, 2.0, 3.0, 6.0], [0.0, 0.0, 0.0, 0.0]])
+    g, b = np.array([1.0, 2.0, 1.0, 1.0]), np.array([0.0, 0.5, 0.0, 0.0])
+    out = R.layer_norm(x, g, b)
+    mu, var = x[0].mean(), x[0].var()
+    np.testing.assert_allclose(out[0], (x[0] - mu) / np.sqrt(var + 1e-12) * g + b, rtol=1e-12)
+    np.testing.assert_allclose(out[1], b)                            # zero-variance row -> beta (eps 1e-12, A.5)
+
+
+def test_edge_order_permutation_invariance_and_linearity():
+    adj, indeg = tiny_graph(29, (80, 29, 40), seed=2)
+    h = node_states(29, 16).astype(np.float64)
+    w = W.rgcn_weights(3, 16, 16)
+    base = R.sparse_rgcn_layer(h, adj, indeg, 16, activation_function="linear", weights=w)
+    rng = np.random.default_rng(0)
+    perm_adj = [a[rng.permutation(a.shape[0])] for a in adj]
+    np.testing.assert_allclose(R.sparse_rgcn_layer(h, perm_adj, indeg, 16, activation_function="linear", weights=w),
+                               base, rtol=1e-10, atol=1e-12)
+    # linear in H before the activation
+    h2 = node_states(29, 16, seed=9).astype(np.float64)
+    s = R.sparse_rgcn_layer(2.0 * h + h2, adj, indeg, 16, activation_function="linear", weights=w)
+    np.testing.assert_allclose(s, 2.0 * base + R.sparse_rgcn_layer(h2, adj, indeg, 16, activation_function="linear",
+                                                                   weights=w), rtol=1e-9, atol=1e-12)
+
+
+def test_rgat_attention_rows_sum_to_one():
+    adj, _ = tiny_graph(31, (70, 31, 20), seed=4)
+    tgt = np.concatenate([a[:, 1] for a in adj])
+    logits = np.random.default_rng(1).standard_normal(tgt.size)
+    att = np.exp(R.unsorted_segment_log_softmax(logits, tgt, 31))
+    sums = R.unsorted_segment_sum(att, tgt, 31)
+    has = np.bincount(tgt, minlength=31) > 0
+    np.testing.assert_allclose(sums[has], 1.0, rtol=1e-12)
+    assert np.all(sums[~has] == 0)
+
+
+def test_film_identity_modulation_reduces_to_rgcn_inside_sum():
+    # gamma = 1, beta = 0 (F_l = 0 gives gamma = beta = 0, so build gamma through a constant feature)
+    adj, indeg = tiny_graph(23, (50, 23), seed=6)
+    D = 8
+    h = node_states(23, D).astype(np.float64)
+    h[:, 0] = 1.0                                                   # constant feature selects a bias row of F_l
+    w = W.film_weights(2, D, D)
+    for l in range(2):
+        f = np.zeros((D, 2 * D)); f[0, :D] = 1.0                   # gamma = 1, beta = 0 for every node
+        w["film_weights"][l] = f
+    film = R.sparse_gnn_film_layer(h, adj, indeg, D, activation_function="relu", weights=w)
+    # same thing by hand: LN( sum relu(W_l h_u) )
+    msgs = np.concatenate([np.maximum(h[a[:, 0]] @ w["edge_weights"][l].astype(np.float64), 0) for l, a in enumerate(adj)])
+    agg = R.unsorted_segment_sum(msgs, np.concatenate([a[:, 1] for a in adj]), 23)
+    np.testing.assert_allclose(film, R.layer_norm(agg, np.ones(D), np.zeros(D)), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", sorted(R.LAYERS))
+def test_fp32_reference_order_close_to_fp64_truth(name):
+    adj, indeg = tiny_graph(41, (120, 41, 60), seed=8)
+    D = 32
+    h = node_states(41, D)
+    kw, w = {}, None
+    if name == "rgcn":
+        w, args = W.rgcn_weights(3, D, D), (indeg, D)
+    elif name == "ggnn":
+        w, args = W.ggnn_weights(3, D), (D,)
+        kw["num_timesteps"] = 2
+    elif name == "rgat":
+        w, args = W.rgat_weights(3, D, D), (D,)
+    elif name == "gnn-film":
+        w, args = W.film_weights(3, D, D), (indeg, D)
+    elif name == "gnn-edge-mlp":
+        w, args = W.edge_mlp_weights(3, D, D), (indeg, D)
+    else:
+        w, args = W.rgin_weights(3, D, D), (D,)
+    o64 = R.LAYERS[name](h, adj, *args, **kw, weights=w)
+    o32 = R.LAYERS[name](h, adj, *args, **kw, weights=w, dtype=np.float32)
+    assert o32.dtype == np.float32
+    assert R.max_norm_rel_err(o32, o64) < 2e-5
