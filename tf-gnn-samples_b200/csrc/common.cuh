@@ -43,16 +43,24 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- device-side activations: utils/utils.py:36-58 ----
-__device__ __forceinline__ float apply_act(float x, int act) {
+// The transcendental activations are kept OUT of line: inlining tanhf/erff/expm1f at every use site
+// (4 components x rows in flight x 2 sites) made the first segment kernel 26k SASS instructions and
+// instruction-fetch bound (profiles/r01_seg_reduce_v1.txt).  relu / linear / leaky_relu stay inline.
+// Each translation unit gets its own copy (static), so no relocatable device code is needed.
+static __device__ __noinline__ float slow_act(float x, int act) {
   switch (act) {
     case RGNN_ACT_TANH: return tanhf(x);
-    case RGNN_ACT_RELU: return fmaxf(x, 0.0f);
-    case RGNN_ACT_LEAKY_RELU: return x > 0.0f ? x : 0.2f * x;            // tf.nn.leaky_relu alpha=0.2
     case RGNN_ACT_ELU: return x > 0.0f ? x : expm1f(x);
     case RGNN_ACT_SELU: return 1.0507009873554805f * (x > 0.0f ? x : 1.6732632423543772f * expm1f(x));
     case RGNN_ACT_GELU: return x * (0.5f * (1.0f + erff(x * 0.70710678118654752f)));  // exact-erf form
-    default: return x;                                                    // linear / None
+    default: return x;
   }
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == RGNN_ACT_LINEAR) return x;
+  if (act == RGNN_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == RGNN_ACT_LEAKY_RELU) return x > 0.0f ? x : 0.2f * x;        // tf.nn.leaky_relu alpha=0.2
+  return slow_act(x, act);
 }
 __device__ __forceinline__ float hard_sigmoid(float x) {                 // Keras hard_sigmoid (TF1 GRU default)
   return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f);

@@ -62,35 +62,40 @@ __device__ __forceinline__ void warp_layer_norm(float4 (&x)[NV], const bool (&ok
     }
 }
 
-template <int NV>
+// NV float4 per lane (the warp covers 128*NV columns starting at blockIdx.y * 128*NV); MODE = MsgMode;
+// MAXAGG = tf.unsorted_segment_max.  Layer-norm epilogues need the whole row in one warp (gridDim.y == 1).
+template <int NV, int MODE, bool MAXAGG>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const __grid_constant__ SegParams p) {
   const int lane = threadIdx.x & 31;
   const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (v >= p.V) return;
+  const int col0 = blockIdx.y * (128 * NV) + lane * 4;
   const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  const bool scaled = p.num_incoming != nullptr;
+  const int act_msg = p.act_msg;
 
   bool ok[NV];
   float4 acc[NV];
-  const float init = (p.agg == RGNN_AGG_MAX) ? -FLT_MAX : 0.0f;   // empty max segment -> lowest() (A.2)
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    ok[k] = (k * 128 + lane * 4) < p.D;
-    acc[k] = f4(init);
+    ok[k] = (col0 + k * 128) < p.D;
+    acc[k] = f4(MAXAGG ? -FLT_MAX : 0.0f);   // empty max segment -> lowest() (A.2)
   }
-
   int cur_type = -1;
   float4 m0[NV], m1[NV];   // gamma/beta (FILM) or q (ADDTGT) of the current (v, type) run
 #pragma unroll
   for (int k = 0; k < NV; ++k) { m0[k] = f4(1.0f); m1[k] = f4(0.0f); }
+  const float* tbase = p.table + col0;
 
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int n = min(32, end - e0);
-    int my_idx = 0, my_type = 0;
+    int my_type = 0;
     float my_scale = 1.0f;
+    long my_off = 0;
     if (lane < n) {
-      my_idx = __ldg(p.e_idx + e0 + lane);
       my_type = __ldg(p.e_type + e0 + lane);
-      if (p.num_incoming != nullptr)   // 1.0f / (c + SMALL_NUMBER) evaluated in fp32 like the reference
+      my_off = (long)__ldg(p.e_idx + e0 + lane) * p.stride_idx + (long)my_type * p.stride_type;
+      if (scaled)   // 1.0f / (c + SMALL_NUMBER) evaluated in fp32 like the reference (rgcn.py:104)
         my_scale = 1.0f / (__ldg(p.num_incoming + (size_t)my_type * p.V + v) + 1e-7f);
     }
     for (int j = 0; j < n; j += UNROLL) {
@@ -98,44 +103,47 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const 
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if (j + u < n) {
-          const int idx = __shfl_sync(0xffffffffu, my_idx, j + u);
-          const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
-          const float* row = p.table + (size_t)idx * p.stride_idx + (size_t)ty * p.stride_type + lane * 4;
+          const long off = __shfl_sync(0xffffffffu, my_off, j + u);
 #pragma unroll
           for (int k = 0; k < NV; ++k)
-            if (ok[k]) r[u][k] = ldg4(row + k * 128);
+            if (ok[k]) r[u][k] = ldg4(tbase + off + k * 128);
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if (j + u < n) {
-          const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
           const float sc = __shfl_sync(0xffffffffu, my_scale, j + u);
-          if (p.msg_mode != MSG_LINEAR && ty != cur_type) {   // warp-uniform: new (v, type) run
-            cur_type = ty;
-            const float* mrow = p.mod_table + (size_t)v * p.mod_stride_node + (size_t)ty * p.mod_stride_type + lane * 4;
+          if (MODE != MSG_LINEAR) {
+            const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
+            if (ty != cur_type) {   // warp-uniform: new (v, type) run
+              cur_type = ty;
+              const float* mrow = p.mod_table + (size_t)v * p.mod_stride_node + (size_t)ty * p.mod_stride_type + col0;
 #pragma unroll
-            for (int k = 0; k < NV; ++k)
-              if (ok[k]) {
-                m0[k] = ldg4(mrow + k * 128);
-                if (p.msg_mode == MSG_FILM) m1[k] = ldg4(mrow + p.D + k * 128);
-              }
+              for (int k = 0; k < NV; ++k)
+                if (ok[k]) {
+                  m0[k] = ldg4(mrow + k * 128);
+                  if (MODE == MSG_FILM) m1[k] = ldg4(mrow + p.D + k * 128);
+                }
+            }
           }
 #pragma unroll
           for (int k = 0; k < NV; ++k)
             if (ok[k]) {
               float4 m = r[u][k];
-              if (p.msg_mode == MSG_LINEAR) {
-                if (p.num_incoming != nullptr) m = mul4(m, sc);
-              } else if (p.msg_mode == MSG_FILM) {
-                if (p.num_incoming != nullptr) m = mul4(m, sc);
-                m = fma4(m0[k], m, m1[k]);
+              if (MODE == MSG_LINEAR) {
+                if (!MAXAGG && act_msg == RGNN_ACT_LINEAR) {   // hot path: acc += s * t as one FMA per element
+                  acc[k].x = fmaf(m.x, sc, acc[k].x); acc[k].y = fmaf(m.y, sc, acc[k].y);
+                  acc[k].z = fmaf(m.z, sc, acc[k].z); acc[k].w = fmaf(m.w, sc, acc[k].w);
+                  continue;
+                }
+                m = mul4(m, sc);
+              } else if (MODE == MSG_FILM) {
+                m = fma4(m0[k], mul4(m, sc), m1[k]);
               } else {
-                m = add4(m, m0[k]);
-                if (p.num_incoming != nullptr) m = mul4(m, sc);
+                m = mul4(add4(m, m0[k]), sc);
               }
-              m = act4(m, p.act_msg);
-              acc[k] = (p.agg == RGNN_AGG_MAX) ? max4(acc[k], m) : add4(acc[k], m);
+              m = act4(m, act_msg);
+              acc[k] = MAXAGG ? max4(acc[k], m) : add4(acc[k], m);
             }
         }
       }
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const 
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc[k] = act4(acc[k], p.act_out);
   if (p.ln_gamma != nullptr) warp_layer_norm<NV>(acc, ok, p.D, lane, p.ln_gamma, p.ln_beta);
-  float* orow = p.out + (size_t)v * p.ld_out + lane * 4;
+  float* orow = p.out + (size_t)v * p.ld_out + col0;
 #pragma unroll
   for (int k = 0; k < NV; ++k)
     if (ok[k]) *reinterpret_cast<float4*>(orow + k * 128) = acc[k];
@@ -311,22 +319,42 @@ inline int nv_for(int D) { return (D + 127) / 128; }
 
 }  // namespace
 
+template <int NV, int MODE>
+static void launch_seg_variant(const SegParams& p, dim3 grid, cudaStream_t stream) {
+  if (p.agg == RGNN_AGG_MAX) seg_reduce_kernel<NV, MODE, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else seg_reduce_kernel<NV, MODE, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+}
+template <int NV>
+static void launch_seg_nv(const SegParams& p, dim3 grid, cudaStream_t stream) {
+  switch (p.msg_mode) {
+    case MSG_FILM: launch_seg_variant<NV, MSG_FILM>(p, grid, stream); break;
+    case MSG_ADDTGT: launch_seg_variant<NV, MSG_ADDTGT>(p, grid, stream); break;
+    default: launch_seg_variant<NV, MSG_LINEAR>(p, grid, stream); break;
+  }
+}
+
 int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
   RGNN_REQUIRE(p.D > 0 && (p.D % 4) == 0, "segment reduce: state dim %d must be a positive multiple of 4", p.D);
-  if (p.D > RGNN_MAX_STATE_DIM) {
-    set_error("segment reduce: state dim %d > %d not supported by this build", p.D, RGNN_MAX_STATE_DIM);
-    return RGNN_E_UNSUPPORTED;
-  }
   RGNN_REQUIRE(p.agg >= RGNN_AGG_SUM && p.agg <= RGNN_AGG_SQRT_N, "Unknown aggregation function code %d", p.agg);
   RGNN_REQUIRE((p.stride_idx % 4) == 0 && (p.stride_type % 4) == 0 && (p.ld_out % 4) == 0 && aligned16(p.table) && aligned16(p.out),
                "segment reduce: rows must be 16-byte aligned");
   if (p.V == 0) return RGNN_OK;
-  const dim3 grid((p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  switch (nv_for(p.D)) {
-    case 1: seg_reduce_kernel<1><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
-    case 2: seg_reduce_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
-    case 3: seg_reduce_kernel<3><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
-    default: seg_reduce_kernel<4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+  const unsigned gx = (p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  if (p.ln_gamma != nullptr) {   // the layer-norm epilogue needs the whole row inside one warp
+    if (p.D > RGNN_MAX_STATE_DIM) {
+      set_error("segment reduce: layer-norm epilogue supports state dim <= %d, got %d", RGNN_MAX_STATE_DIM, p.D);
+      return RGNN_E_UNSUPPORTED;
+    }
+    const dim3 grid(gx, 1);
+    switch (nv_for(p.D)) {
+      case 1: launch_seg_nv<1>(p, grid, stream); break;
+      case 2: launch_seg_nv<2>(p, grid, stream); break;
+      case 3: launch_seg_nv<3>(p, grid, stream); break;
+      default: launch_seg_nv<4>(p, grid, stream); break;
+    }
+  } else {                       // otherwise one warp per 128-column slice of a target row: more rows in flight
+    const dim3 grid(gx, (p.D + 127) / 128);
+    launch_seg_nv<1>(p, grid, stream);
   }
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
