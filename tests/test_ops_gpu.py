@@ -1,0 +1,64 @@
+"""GPU: the exported building blocks against numpy (float64): tcgen05 3xTF32 Dense at awkward shapes,
+segment aggregation in all four modes, layer norm."""
+import numpy as np
+import pytest
+
+from oracle import ref_layers as R
+from tf_gnn_samples_b200 import GraphPlan, ops
+
+from helpers import assert_parity, tiny_graph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 4, 4), (129, 36, 52), (300, 64, 96), (2245, 256, 768), (511, 320, 1280),
+                                   (64, 512, 16), (1000, 8, 264), (4100, 128, 384)])
+def test_dense_matches_fp64(cuda_device, m, k, n):
+    import torch
+    rng = np.random.default_rng(m * 7 + n)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    got = ops.dense(torch.as_tensor(a).to(cuda_device), torch.as_tensor(w).to(cuda_device)).cpu().numpy()
+    want = a.astype(np.float64) @ w.astype(np.float64)
+    err = assert_parity(got, want, "dense %dx%dx%d" % (m, k, n), tol=2e-6)   # 3xTF32: fp32-level accuracy
+    print("dense %dx%dx%d max-norm rel err %.2e" % (m, k, n, err))
+
+
+def test_dense_bias_activation(cuda_device):
+    import torch
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((77, 48)).astype(np.float32)
+    w = rng.standard_normal((48, 40)).astype(np.float32) / 7
+    b = rng.standard_normal(40).astype(np.float32)
+    for act in ["tanh", "relu", "gelu", None]:
+        got = ops.dense(torch.as_tensor(a).to(cuda_device), torch.as_tensor(w).to(cuda_device),
+                        torch.as_tensor(b).to(cuda_device), act).cpu().numpy()
+        want = a.astype(np.float64) @ w.astype(np.float64) + b
+        fn = R.get_activation(act)
+        want = want if fn is None else fn(want)
+        assert_parity(got, want, "dense+bias+%s" % act, tol=1e-5)
+
+
+@pytest.mark.parametrize("agg", ["sum", "max", "mean", "sqrt_n"])
+def test_segment_aggregate(cuda_device, agg):
+    import torch
+    adj, _ = tiny_graph(40, (90, 0, 33), seed=5, with_isolated=False)
+    adj[1] = np.zeros((0, 2), np.int32)
+    adj.append(np.stack([np.arange(40), np.arange(40)], axis=1).astype(np.int32))   # every node has a message
+    plan = GraphPlan(adj, 40, device=cuda_device)
+    tgt = np.concatenate([a[:, 1] for a in adj])
+    data = np.random.default_rng(1).standard_normal((tgt.size, 20)).astype(np.float32)
+    got = ops.segment_aggregate(plan, torch.as_tensor(data).to(cuda_device), agg).cpu().numpy()
+    want = R.get_aggregation_function(agg)(data.astype(np.float64), tgt, 40)
+    assert_parity(got, want, "segment %s" % agg, tol=1e-6)
+
+
+def test_layer_norm(cuda_device):
+    import torch
+    rng = np.random.default_rng(2)
+    for d in (8, 128, 300, 512):
+        x = rng.standard_normal((33, d)).astype(np.float32) * 3 + 1
+        x[5] = 0.0                                                              # zero-variance row -> beta
+        g, b = rng.standard_normal(d).astype(np.float32), rng.standard_normal(d).astype(np.float32)
+        got = ops.layer_norm(*(torch.as_tensor(t).to(cuda_device) for t in (x, g, b))).cpu().numpy()
+        assert_parity(got, R.layer_norm(x.astype(np.float64), g, b), "layer_norm d=%d" % d, tol=1e-5)

@@ -42,6 +42,17 @@ struct GemmParams {
 };
 
 // Enqueue; returns RGNN_OK / error code.  All dims % 4 == 0, pointers 16-byte aligned.
+// Legacy tensor path (mma.sync.m16n8k8.tf32): kept as the A/B reference of the tcgen05 kernel
+// (RGNN_GEMM_IMPL=mma); needs no scratch.
 int launch_gemm(const GemmParams& p, cudaStream_t stream);
+
+// Blackwell path (gemm_tcgen05.cu): tcgen05.mma.kind::tf32 with a TMEM accumulator.  Needs scratch for
+// the pre-swizzled hi/lo weight images (gemm_tc_pack_bytes).  The scratch may be reused as soon as the call
+// returns as long as later users are ordered on the same stream.
+size_t gemm_tc_pack_bytes(const GemmParams& p);
+int launch_gemm_tcgen05(const GemmParams& p, void* pack_ws, size_t pack_ws_bytes, cudaStream_t stream);
+
+// true unless the environment says RGNN_GEMM_IMPL=mma
+bool gemm_use_tcgen05();
 
 }  // namespace rgnn

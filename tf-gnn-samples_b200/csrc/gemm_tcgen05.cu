@@ -1,0 +1,445 @@
+// gemm_tcgen05.cu -- C = epilogue([A1|A2] . [B1;B2]) on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Same contract as gemm_tf32x3.cu (fp32 in / fp32 out, fp32-level accuracy through 3xTF32 split
+// accumulation), but on the Blackwell-native path: the legacy mma.sync TF32 pipe tops out at
+// ~240 TFLOP/s on B200 (profiles/r01_gemm_mma_sync.txt), i.e. 3xTF32 there is no faster than FFMA.
+//
+//   * accumulator: 128 x BN fp32 tile in TMEM (tcgen05.alloc), BN in {32..256} chosen per problem so the
+//     grid is ~one wave of 148 CTAs;
+//   * operands: K-major SWIZZLE_128B shared-memory images, one 128-byte row = 32 fp32 of K;
+//       B (weights): split into TF32 hi/lo and pre-swizzled ONCE per call by pack_b_kernel into the exact
+//         shared-memory image, then streamed with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) that
+//         complete on the stage's mbarrier;
+//       A (node states): 4 producer warps load rows with coalesced 128-bit loads, split hi/lo in
+//         registers and store both images swizzled (conflict-free), then fence.proxy.async + arrive;
+//   * MMA: one elected thread issues, per 32-wide K chunk, 4 k-steps x {lo*hi, hi*lo, hi*hi}
+//     tcgen05.mma.kind::tf32 into the same TMEM accumulator, and tcgen05.commit releases the stage;
+//   * epilogue: the 4 producer warps read their 32 TMEM lanes with tcgen05.ld.32x32b.x16, apply
+//     bias / activation / GRU gate math and store rows.
+#include "gemm.cuh"
+
+namespace rgnn {
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                    // fp32 elements per 128-byte swizzle row
+constexpr int TC_PRODUCER_WARPS = 4;
+constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + 2);   // + MMA warp + B-loader warp
+constexpr int A_IMG_BYTES = TC_BM * 128;     // 16 KB
+constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must fault the kernel (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start>>4 | LBO | SBO=1024B | version 1 | layout 2.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // bits [0,14)  start address >> 4
+  d |= (uint64_t)1 << 16;                                // bits [16,30) leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                      // bits [32,46) stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                                // bits [46,48) descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                                // bits [61,64) SWIZZLE_128B
+  return d;
+}
+
+// kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);   // exactly representable in TF32
+  lo = x - hi;                                              // exact in fp32; the tensor core keeps its top 11 bits
+}
+
+// -------------------------------------------------------------------------------------------------
+// pack_b: [K, N] fp32 weights -> per (n-tile, k-chunk) hi / lo shared-memory images (BN rows x 128 B,
+// K-major, 128-byte swizzled).  Column blocks may come from different matrices (per-type kernels).
+// -------------------------------------------------------------------------------------------------
+struct PackParams {
+  const float* b1[RGNN_MAX_EDGE_TYPES];   // column block j of segment 1: rows [0, K1)
+  const float* b2[RGNN_MAX_EDGE_TYPES];   // column block j of segment 2: rows [0, K2) (may be null when K2 == 0)
+  int ldb1, ldb2;
+  int K1, K2;
+  int block_cols;                         // width of one column block (N for a plain GEMM)
+  int n_total;                            // total columns = blocks * block_cols
+  int BN;
+  int chunks1, chunks2;                   // ceil(K1/32), ceil(K2/32)
+  float* out;                             // [n_tiles][chunks1+chunks2][2][BN*32]
+};
+
+__global__ void __launch_bounds__(256) pack_b_kernel(const __grid_constant__ PackParams p) {
+  const int chunk = blockIdx.x;           // k-chunk over both segments
+  const int tile = blockIdx.y;            // n-tile
+  const int nchunks = p.chunks1 + p.chunks2;
+  const bool seg2 = chunk >= p.chunks1;
+  const int k0 = (seg2 ? chunk - p.chunks1 : chunk) * TC_BK;
+  const int Kseg = seg2 ? p.K2 : p.K1;
+  const int ld = seg2 ? p.ldb2 : p.ldb1;
+  float* img_hi = p.out + ((size_t)tile * nchunks + chunk) * 2 * (p.BN * TC_BK);
+  float* img_lo = img_hi + p.BN * TC_BK;
+  for (int i = threadIdx.x; i < p.BN * 8; i += blockDim.x) {
+    const int nl = i % p.BN;              // consecutive threads -> consecutive n: coalesced reads per k
+    const int c16 = i / p.BN;             // 16-byte chunk (4 k values) inside the 128-byte row
+    const int n = tile * p.BN + nl;
+    float hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + c16 * 4 + j;
+      float x = 0.0f;
+      if (n < p.n_total && k < Kseg) {
+        const int blk = n / p.block_cols, col = n - blk * p.block_cols;
+        const float* src = seg2 ? p.b2[blk] : p.b1[blk];
+        x = __ldg(src + (size_t)k * ld + col);
+      }
+      split_tf32(x, hi[j], lo[j]);
+    }
+    const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((c16 ^ (nl & 7)) << 2);   // float index inside the image
+    *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+struct TcParams {
+  GemmParams g;
+  const float* packed;     // pack_b output (per z for ROW_RANGES / COL_BLOCKS: z * packed_stride floats)
+  size_t packed_stride;
+  int BN, stages, chunks1, chunks2;
+  int n_total;             // columns of C covered by this launch (batch*N for SHARED_A, else N)
+  int tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const GemmParams& g = p.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN, S = p.stages;
+  const int b_img_bytes = BN * 128;
+  const int stage_bytes = 2 * A_IMG_BYTES + 2 * b_img_bytes;
+  // 1024-byte aligned operand ring, then barriers
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_bytes);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accum_bar = smem_u32(bars + 2 * S);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+
+  // ---- operands of this CTA ----
+  const int z = blockIdx.z;
+  const float* A1 = g.A1;
+  float* C = g.C;
+  int row_begin = 0, row_end = g.M;
+  const float* packed = p.packed;
+  if (g.batch_mode == BATCH_ROW_RANGES) {
+    row_begin = g.row_off[z]; row_end = g.row_off[z + 1];
+    packed += (size_t)z * p.packed_stride;
+  } else if (g.batch_mode == BATCH_COL_BLOCKS) {
+    A1 += (size_t)z * g.K1;
+    C += (size_t)z * g.N;
+    packed += (size_t)z * p.packed_stride;
+  }
+  const int m0 = row_begin + blockIdx.y * TC_BM;
+  if (m0 >= row_end) return;                       // uniform across the CTA, before any barrier / allocation
+  const int n_tile = blockIdx.x, n0 = n_tile * BN;
+  const int nchunks = p.chunks1 + p.chunks2;
+
+  if (warp == TC_PRODUCER_WARPS && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, TC_PRODUCER_WARPS * 32 + 1);   // 128 producer arrivals + the B loader's expect_tx arrival
+      mbar_init(empty0 + 8 * s, 1);                           // one tcgen05.commit
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == TC_PRODUCER_WARPS) {                  // TMEM allocation by the MMA warp (it also frees it)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // =========================== A producers ===========================
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % S;
+      const uint32_t use = c / S;
+      if (c >= S) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
+      const bool seg2 = c >= p.chunks1;
+      const int k0 = (seg2 ? c - p.chunks1 : c) * TC_BK;
+      const int Kseg = seg2 ? g.K2 : g.K1;
+      const float* Abase = seg2 ? g.A2 : A1;
+      const int lda = seg2 ? g.lda2 : g.lda1;
+      uint8_t* a_hi = ring + (size_t)s * stage_bytes;
+      uint8_t* a_lo = a_hi + A_IMG_BYTES;
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                 // all 8 loads first (memory-level parallelism)
+        const int f = tid + i * (TC_PRODUCER_WARPS * 32);
+        const int row = f >> 3, c16 = f & 7;
+        const int grow = m0 + row, gk = k0 + c16 * 4;
+        v[i] = (grow < row_end && gk < Kseg) ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)grow * lda + gk))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int f = tid + i * (TC_PRODUCER_WARPS * 32);
+        const int row = f >> 3, c16 = f & 7;
+        float4 hi, lo;
+        split_tf32(v[i].x, hi.x, lo.x); split_tf32(v[i].y, hi.y, lo.y);
+        split_tf32(v[i].z, hi.z, lo.z); split_tf32(v[i].w, hi.w, lo.w);
+        const int off = row * 128 + ((c16 ^ (row & 7)) << 4);
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
+      }
+      fence_proxy_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full0 + 8 * s);
+    }
+    // =========================== epilogue ===========================
+    mbar_wait(accum_bar, 0);
+    __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
+    tc_fence_after_sync();
+    const int r = m0 + warp * 32 + lane;            // TMEM lane == tile row; warp w owns lanes [32w, 32w+32)
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int dgru = (g.epi == EPI_GRU_ZR) ? g.N / 2 : g.N;
+    for (int cb = 0; cb < BN; cb += 16) {
+      float v[16];
+      tmem_ld16(lane_base + cb, v);                 // warp-collective: every lane executes it
+      const int c0 = n0 + cb;
+      if (r >= row_end || c0 >= p.n_total) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c0 + q * 4;
+        if (c >= p.n_total) break;
+        float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        if (g.bias != nullptr) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (g.epi == EPI_STORE) {
+          o = act4(o, g.act);
+          *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = o;
+        } else if (g.epi == EPI_GRU_ZR) {
+          o.x = hard_sigmoid(o.x); o.y = hard_sigmoid(o.y); o.z = hard_sigmoid(o.z); o.w = hard_sigmoid(o.w);
+          if (c < dgru) {
+            *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = o;                      // z gate
+          } else {
+            const int cc = c - dgru;
+            const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + cc));
+            *reinterpret_cast<float4*>(g.C2 + (size_t)r * g.ldc2 + cc) = make_float4(o.x * h.x, o.y * h.y, o.z * h.z, o.w * h.w);
+          }
+        } else {  // EPI_GRU_OUT: h' = z*h + (1-z)*act(.)
+          o = act4(o, g.act);
+          const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + c));
+          const float4 zz = __ldg(reinterpret_cast<const float4*>(g.aux_z + (size_t)r * g.ld_z + c));
+          *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) =
+              make_float4(zz.x * h.x + (1.0f - zz.x) * o.x, zz.y * h.y + (1.0f - zz.y) * o.y,
+                          zz.z * h.z + (1.0f - zz.z) * o.z, zz.w * h.w + (1.0f - zz.w) * o.w);
+        }
+      }
+    }
+  } else if (warp == TC_PRODUCER_WARPS) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % S;
+        mbar_wait(full0 + 8 * s, (c / S) & 1);
+        tc_fence_after_sync();
+        const uint32_t a_hi = smem_u32(ring + (size_t)s * stage_bytes);
+        const uint32_t a_lo = a_hi + A_IMG_BYTES;
+        const uint32_t b_hi = a_lo + A_IMG_BYTES;
+        const uint32_t b_lo = b_hi + b_img_bytes;
+        const uint64_t da_hi = make_sw128_desc(a_hi), da_lo = make_sw128_desc(a_lo);
+        const uint64_t db_hi = make_sw128_desc(b_hi), db_lo = make_sw128_desc(b_lo);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {       // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (>>4 units)
+          const uint64_t adv = (uint64_t)(k * 2);
+          umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (c | k) != 0);   // small terms first
+          umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1);
+          umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1);
+        }
+        umma_commit(empty0 + 8 * s);                // stage reusable once these MMAs have read it
+      }
+      umma_commit(accum_bar);                       // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else {
+    // =========================== B loader (TMA bulk copies of the packed images) ===========================
+    if (lane == 0) {
+      const float* src_tile = packed + (size_t)n_tile * nchunks * 2 * (BN * TC_BK);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % S;
+        if (c >= S) mbar_wait(empty0 + 8 * s, ((c / S) - 1) & 1);
+        const uint32_t b_hi = smem_u32(ring + (size_t)s * stage_bytes + 2 * A_IMG_BYTES);
+        mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);
+        bulk_copy_g2s(b_hi, src_tile + (size_t)c * 2 * (BN * TC_BK), 2 * b_img_bytes, full0 + 8 * s);   // hi and lo are adjacent
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- teardown ----
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == TC_PRODUCER_WARPS) {
+    tc_fence_after_sync();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+int pick_bn(long m_tiles, int n_total, int gz) {
+  int best = 32;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 32; bn -= 16) {
+    const long ctas = m_tiles * ((n_total + bn - 1) / bn) * gz;
+    const long waves = (ctas + 147) / 148;
+    const double cost = (double)waves * (96.0 + bn);   // per-tile time ~ fixed overhead + columns
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+size_t gemm_tc_pack_bytes(const GemmParams& g) {
+  const int chunks = (g.K1 + TC_BK - 1) / TC_BK + (g.K2 + TC_BK - 1) / TC_BK;
+  const int n_total = (g.batch_mode == BATCH_SHARED_A) ? g.batch * g.N : g.N;
+  const int gz = (g.batch_mode == BATCH_ROW_RANGES || g.batch_mode == BATCH_COL_BLOCKS) ? g.batch : 1;
+  const int rows = (g.batch_mode == BATCH_ROW_RANGES) ? g.max_rows : g.M;
+  const int bn = pick_bn((rows + TC_BM - 1) / TC_BM, n_total, gz);
+  const size_t tiles = (n_total + bn - 1) / bn;
+  return align_up(tiles * chunks * 2 * (size_t)bn * TC_BK * sizeof(float) * gz, 1024);
+}
+
+int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes, cudaStream_t stream) {
+  RGNN_REQUIRE(g.M >= 0 && g.N > 0 && g.K1 > 0 && g.K2 >= 0, "gemm: bad dims M=%d N=%d K1=%d K2=%d", g.M, g.N, g.K1, g.K2);
+  RGNN_REQUIRE((g.N % 4) == 0 && (g.K1 % 4) == 0 && (g.K2 % 4) == 0, "gemm: N, K must be multiples of 4 (N=%d K1=%d K2=%d)", g.N, g.K1, g.K2);
+  RGNN_REQUIRE((g.lda1 % 4) == 0 && (g.ldb1 % 4) == 0 && (g.ldc % 4) == 0, "gemm: leading dims must keep 16-byte rows");
+  RGNN_REQUIRE(g.batch >= 1 && g.batch <= RGNN_MAX_EDGE_TYPES, "gemm: batch %d out of range", g.batch);
+  RGNN_REQUIRE(aligned16(g.A1) && aligned16(g.C) && (g.K2 == 0 || aligned16(g.A2)), "gemm: operands must be 16-byte aligned");
+  RGNN_REQUIRE(g.bias == nullptr || aligned16(g.bias), "gemm: bias must be 16-byte aligned");
+  const int rows = (g.batch_mode == BATCH_ROW_RANGES) ? g.max_rows : g.M;
+  if (rows <= 0) return RGNN_OK;
+  const size_t need = gemm_tc_pack_bytes(g);
+  RGNN_REQUIRE(pack_ws != nullptr && pack_ws_bytes >= need && (reinterpret_cast<uintptr_t>(pack_ws) & 15u) == 0,
+               "gemm: weight-image workspace too small (%zu < %zu)", pack_ws_bytes, need);
+
+  TcParams p;
+  p.g = g;
+  p.chunks1 = (g.K1 + TC_BK - 1) / TC_BK;
+  p.chunks2 = (g.K2 + TC_BK - 1) / TC_BK;
+  const int nchunks = p.chunks1 + p.chunks2;
+  p.n_total = (g.batch_mode == BATCH_SHARED_A) ? g.batch * g.N : g.N;
+  const int gz = (g.batch_mode == BATCH_ROW_RANGES || g.batch_mode == BATCH_COL_BLOCKS) ? g.batch : 1;
+  p.BN = pick_bn((rows + TC_BM - 1) / TC_BM, p.n_total, gz);
+  const int n_tiles = (p.n_total + p.BN - 1) / p.BN;
+  const size_t stage_bytes = 2 * (size_t)A_IMG_BYTES + 2 * (size_t)p.BN * 128;
+  p.stages = (int)(TC_SMEM_BUDGET / stage_bytes);
+  if (p.stages > 4) p.stages = 4;
+  if (p.stages > nchunks) p.stages = nchunks;
+  if (p.stages < 1) p.stages = 1;
+  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  p.packed = static_cast<const float*>(pack_ws);
+  p.packed_stride = (size_t)n_tiles * nchunks * 2 * p.BN * TC_BK;
+
+  // ---- pack the weights into shared-memory images ----
+  for (int zz = 0; zz < gz; ++zz) {
+    PackParams q;
+    q.ldb1 = g.ldb1; q.ldb2 = g.ldb2; q.K1 = g.K1; q.K2 = g.K2;
+    q.BN = p.BN; q.chunks1 = p.chunks1; q.chunks2 = p.chunks2;
+    q.n_total = p.n_total;
+    if (g.batch_mode == BATCH_SHARED_A) {
+      q.block_cols = g.N;
+      for (int j = 0; j < g.batch; ++j) { q.b1[j] = g.bptr[j]; q.b2[j] = g.bptr2[j]; }
+    } else if (g.batch_mode == BATCH_NONE) {
+      q.block_cols = g.N; q.b1[0] = g.B1; q.b2[0] = g.B2;
+    } else {
+      q.block_cols = g.N; q.b1[0] = g.bptr[zz]; q.b2[0] = g.bptr2[zz];
+    }
+    for (int j = 0; j < (g.batch_mode == BATCH_SHARED_A ? g.batch : 1); ++j) {
+      RGNN_REQUIRE(q.b1[j] != nullptr && (g.K2 == 0 || q.b2[j] != nullptr), "gemm: weight pointer %d is NULL", j);
+    }
+    q.out = static_cast<float*>(pack_ws) + (size_t)zz * p.packed_stride;
+    pack_b_kernel<<<dim3(nchunks, n_tiles), 256, 0, stream>>>(q);
+    RGNN_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    attr_smem = 220 * 1024;
+  }
+  dim3 grid(n_tiles, (rows + TC_BM - 1) / TC_BM, gz);
+  gemm_tcgen05_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+}  // namespace rgnn

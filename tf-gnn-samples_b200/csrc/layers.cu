@@ -9,6 +9,7 @@
 #include <mutex>
 #include <atomic>
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -66,6 +67,18 @@ int check_agg(int agg, const char* who) {
   RGNN_REQUIRE(agg >= RGNN_AGG_SUM && agg <= RGNN_AGG_SQRT_N, "%s: Unknown aggregation function code %d", who, agg);
   return RGNN_OK;
 }
+bool g_use_tc = true;
+bool g_use_tc_init = false;
+}  // namespace
+bool gemm_use_tcgen05() {
+  if (!g_use_tc_init) {
+    const char* e = getenv("RGNN_GEMM_IMPL");
+    g_use_tc = !(e != nullptr && strcmp(e, "mma") == 0);
+    g_use_tc_init = true;
+  }
+  return g_use_tc;
+}
+namespace {
 int check_ws(const Arena& a, const char* who) {
   if (a.overflow) {
     set_error("%s: workspace too small (%zu bytes given, %zu needed)", who, a.cap, a.used);
@@ -74,8 +87,24 @@ int check_ws(const Arena& a, const char* who) {
   return RGNN_OK;
 }
 
+// Dispatch one dense contraction: tcgen05 kernel (weight images packed into arena scratch that is released
+// right after the enqueue -- later users are stream-ordered) or the legacy mma.sync kernel.
+int run_gemm(const GemmParams& g, Arena& ar, cudaStream_t stream) {
+  if (!gemm_use_tcgen05()) return launch_gemm(g, stream);
+  const size_t need = gemm_tc_pack_bytes(g);
+  const size_t mark = ar.used;
+  void* ws = ar.floats(need / sizeof(float));
+  if (ar.overflow) {
+    set_error("workspace too small for the weight images of a dense contraction (%zu bytes given, %zu needed)", ar.cap, ar.used);
+    return RGNN_E_WORKSPACE;
+  }
+  const int rc = launch_gemm_tcgen05(g, ws, need, stream);
+  ar.used = mark;
+  return rc;
+}
+
 // T[V, batch*N] = A[V, K] . B_z  for z < batch  (shared A)
-int gemm_shared_a(const float* A, int V, int K, const float* const* B, int batch, int ldb, int N, float* C, int act,
+int gemm_shared_a(Arena& ar, const float* A, int V, int K, const float* const* B, int batch, int ldb, int N, float* C, int act,
                   cudaStream_t stream) {
   GemmParams g;
   g.A1 = A; g.lda1 = K; g.K1 = K;
@@ -85,7 +114,7 @@ int gemm_shared_a(const float* A, int V, int K, const float* const* B, int batch
   g.act = act;
   g.batch_mode = BATCH_SHARED_A; g.batch = batch;
   for (int z = 0; z < batch; ++z) { g.bptr[z] = B[z]; g.bptr2[z] = nullptr; }
-  return launch_gemm(g, stream);
+  return run_gemm(g, ar, stream);
 }
 
 void seg_from_plan(SegParams& s, const rgnn_plan_t* plan) {
@@ -141,7 +170,7 @@ int build_mlp_messages(const rgnn_plan_t* plan, const float* cur, int d_in, cons
     float* prev = ar.floats((size_t)V * L * dims[1]);
     if (ar.overflow) { *out = ms; return RGNN_OK; }
     for (int l = 0; l < L; ++l) bp[l] = kernels[l * nl + 0];
-    RGNN_PROPAGATE(gemm_shared_a(cur, V, d_in, bp, L, dims[1], dims[1], prev, nl > 1 ? hidden_act : RGNN_ACT_LINEAR, stream));
+    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, d_in, bp, L, dims[1], dims[1], prev, nl > 1 ? hidden_act : RGNN_ACT_LINEAR, stream));
     for (int j = 1; j < nl; ++j) {
       float* next = ar.floats((size_t)V * L * dims[j + 1]);
       if (ar.overflow) { *out = ms; return RGNN_OK; }
@@ -151,7 +180,7 @@ int build_mlp_messages(const rgnn_plan_t* plan, const float* cur, int d_in, cons
       g.act = (j < nl - 1) ? hidden_act : RGNN_ACT_LINEAR;
       g.batch_mode = BATCH_COL_BLOCKS; g.batch = L;
       for (int l = 0; l < L; ++l) { g.bptr[l] = kernels[l * nl + j]; g.bptr2[l] = nullptr; }
-      RGNN_PROPAGATE(launch_gemm(g, stream));
+      RGNN_PROPAGATE(run_gemm(g, ar, stream));
       prev = next;
     }
     ms.table = prev; ms.idx = plan->e_src; ms.stride_idx = (long)L * dims[nl]; ms.stride_type = dims[nl]; ms.width = dims[nl];
@@ -167,7 +196,7 @@ int build_mlp_messages(const rgnn_plan_t* plan, const float* cur, int d_in, cons
     bp[l] = kernels[l * nl + 0];                              // rows [0, d_in)      multiply h_u
     bp[L + l] = kernels[l * nl + 0] + (size_t)d_in * d1;      // rows [d_in, 2 d_in) multiply h_v
   }
-  RGNN_PROPAGATE(gemm_shared_a(cur, V, d_in, bp, 2 * L, d1, d1, PQ, RGNN_ACT_LINEAR, stream));
+  RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, d_in, bp, 2 * L, d1, d1, PQ, RGNN_ACT_LINEAR, stream));
   if (nl == 1) {
     ms.table = PQ; ms.idx = plan->e_src; ms.stride_idx = 2L * L * d1; ms.stride_type = d1; ms.width = d1;
     ms.msg_mode = MSG_ADDTGT; ms.mod_table = PQ + (size_t)L * d1; ms.mod_sn = 2L * L * d1; ms.mod_st = d1;
@@ -196,7 +225,7 @@ int build_mlp_messages(const rgnn_plan_t* plan, const float* cur, int d_in, cons
     g.batch_mode = BATCH_ROW_RANGES; g.batch = L; g.max_rows = plan->max_type_edges;
     for (int l = 0; l < L; ++l) { g.bptr[l] = kernels[l * nl + j]; g.bptr2[l] = nullptr; g.row_off[l] = plan->type_off[l]; }
     g.row_off[L] = plan->type_off[L];
-    RGNN_PROPAGATE(launch_gemm(g, stream));
+    RGNN_PROPAGATE(run_gemm(g, ar, stream));
     prev = next;
   }
   ms.table = prev; ms.idx = plan->e_orig; ms.stride_idx = dims[nl]; ms.stride_type = 0; ms.width = dims[nl];
@@ -239,7 +268,9 @@ extern "C" size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, 
     }
     default: return 0;
   }
-  return floats * sizeof(float) + pad;
+  // scratch for the pre-swizzled hi/lo weight images of the largest dense contraction of the layer
+  const size_t pack = 2 * (2 * dm + 64) * (2 * L * dm + 2 * dm + 512);
+  return (floats + pack) * sizeof(float) + pad;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -274,7 +305,7 @@ extern "C" int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* h, int32_
       bp[l] = edge_weights[l];                                                // kernel rows [0, d_in): source half
       if (both) bp[L + l] = edge_weights[l] + (size_t)din * d_out;            // rows [d_in, 2 d_in): target half (rgcn.py:95)
     }
-    RGNN_PROPAGATE(gemm_shared_a(cur, V, din, bp, nb, d_out, d_out, T, RGNN_ACT_LINEAR, stream));   // rgcn.py:98 on nodes
+    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, bp, nb, d_out, d_out, T, RGNN_ACT_LINEAR, stream));   // rgcn.py:98 on nodes
     SegParams s;
     seg_from_plan(s, plan);
     s.D = d_out; s.table = T; s.stride_idx = (long)nb * d_out; s.stride_type = d_out;
@@ -320,7 +351,7 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
   const float* cur = h;
   for (int t = 0; t < num_timesteps; ++t) {                                   // ggnn.py:71
     float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
-    RGNN_PROPAGATE(gemm_shared_a(cur, V, D, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));   // ggnn.py:80-82
+    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, D, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));   // ggnn.py:80-82
     SegParams s;
     seg_from_plan(s, plan);
     s.D = D; s.table = T; s.stride_idx = (long)L * D; s.stride_type = D;
@@ -333,20 +364,20 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
       g.A2 = cur; g.lda2 = D; g.K2 = D;
       g.B1 = cell_kernel; g.ldb1 = D; g.B2 = cell_recurrent_kernel; g.ldb2 = D;
       g.N = D; g.C = dst; g.ldc = D; g.epi = EPI_STORE; g.act = activation;
-      RGNN_PROPAGATE(launch_gemm(g, stream));
+      RGNN_PROPAGATE(run_gemm(g, ar, stream));
     } else {                                                                  // GRUCell, gates z|r|h (A.4)
       g.A2 = cur; g.lda2 = D; g.K2 = D;
       g.B1 = cell_kernel; g.ldb1 = 3 * D; g.B2 = cell_recurrent_kernel; g.ldb2 = 3 * D;
       g.N = 2 * D; g.C = z; g.ldc = D; g.C2 = rh; g.ldc2 = D; g.aux_h = cur; g.ld_h = D;
       g.epi = EPI_GRU_ZR;
-      RGNN_PROPAGATE(launch_gemm(g, stream));
+      RGNN_PROPAGATE(run_gemm(g, ar, stream));
       GemmParams o;
       o.A1 = m; o.lda1 = D; o.K1 = D; o.A2 = rh; o.lda2 = D; o.K2 = D;
       o.B1 = cell_kernel + 2 * D; o.ldb1 = 3 * D; o.B2 = cell_recurrent_kernel + 2 * D; o.ldb2 = 3 * D;
       o.M = V; o.N = D; o.bias = cell_bias + 2 * D; o.C = dst; o.ldc = D;
       o.aux_h = cur; o.ld_h = D; o.aux_z = z; o.ld_z = D;
       o.epi = EPI_GRU_OUT; o.act = activation;
-      RGNN_PROPAGATE(launch_gemm(o, stream));
+      RGNN_PROPAGATE(run_gemm(o, ar, stream));
     }
     cur = dst;
   }
@@ -383,7 +414,7 @@ extern "C" int rgnn_rgat_forward(const rgnn_plan_t* plan, const float* h, int32_
   int din = d_in;
   for (int t = 0; t < num_timesteps; ++t) {                                   // rgat.py:83
     float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
-    RGNN_PROPAGATE(gemm_shared_a(cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));   // rgat.py:95-96
+    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));   // rgat.py:95-96
     RGNN_PROPAGATE(launch_rgat_scores(T, V, L, D, K, at, ssrc, stgt, stream));                      // rgat.py:106-115 (per node)
     RgatParams r;
     r.V = V; r.L = L; r.D = D; r.K = K;
@@ -423,8 +454,8 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
   int din = d_in;
   for (int t = 0; t < num_timesteps; ++t) {                                   // gnn_film.py:85
     float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
-    RGNN_PROPAGATE(gemm_shared_a(cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));        // :94 on nodes
-    RGNN_PROPAGATE(gemm_shared_a(cur, V, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));  // :102
+    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));        // :94 on nodes
+    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));  // :102
     SegParams s;
     seg_from_plan(s, plan);
     s.D = D; s.table = T; s.stride_idx = (long)L * D; s.stride_type = D;
@@ -545,7 +576,7 @@ extern "C" int rgnn_rgin_forward(const rgnn_plan_t* plan, const float* h, int32_
         g.B1 = aggr_kernels[j]; g.ldb1 = aggr_dims[j + 1];
         g.M = V; g.N = aggr_dims[j + 1]; g.C = next; g.ldc = aggr_dims[j + 1];
         g.act = activation;   // hidden layers: MLP activation (rgin.py:80); last layer: the explicit activation of :138
-        RGNN_PROPAGATE(launch_gemm(g, stream));
+        RGNN_PROPAGATE(run_gemm(g, ar, stream));
         prev = next;
       }
       RGNN_PROPAGATE(launch_layer_norm(prev, V, D, ln_gamma + (size_t)t * D, ln_beta + (size_t)t * D, dst, stream));  // :139
@@ -578,7 +609,13 @@ extern "C" int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const fl
   GemmParams g;
   g.A1 = a; g.lda1 = k; g.K1 = k; g.B1 = b; g.ldb1 = n; g.M = m; g.N = n; g.C = c; g.ldc = n;
   g.bias = bias; g.act = activation;
-  return launch_gemm(g, stream);
+  if (!gemm_use_tcgen05()) return launch_gemm(g, stream);
+  const size_t need = gemm_tc_pack_bytes(g);
+  void* ws = nullptr;
+  RGNN_CHECK_CUDA(cudaMallocAsync(&ws, need, stream));
+  const int rc = launch_gemm_tcgen05(g, ws, need, stream);
+  cudaFreeAsync(ws, stream);
+  return rc;
 }
 
 extern "C" int rgnn_layer_norm(const float* x, int32_t rows, int32_t d, const float* gamma, const float* beta,
