@@ -18,6 +18,10 @@
 //     bias / activation / GRU gate math and store rows.
 #include "gemm.cuh"
 
+#include <stdlib.h>
+#include <vector>
+#include <algorithm>
+
 namespace rgnn {
 
 namespace {
@@ -130,6 +134,7 @@ struct PackParams {
   float* out;                             // [n_tiles][chunks1+chunks2][2][BN*32]
 };
 
+// grid = (k-chunks, n-tiles, BN/32 row slices... ceil), block = 256 threads = 32 image rows x 8 16-byte chunks
 __global__ void __launch_bounds__(256) pack_b_kernel(const __grid_constant__ PackParams p) {
   const int chunk = blockIdx.x;           // k-chunk over both segments
   const int tile = blockIdx.y;            // n-tile
@@ -140,26 +145,26 @@ __global__ void __launch_bounds__(256) pack_b_kernel(const __grid_constant__ Pac
   const int ld = seg2 ? p.ldb2 : p.ldb1;
   float* img_hi = p.out + ((size_t)tile * nchunks + chunk) * 2 * (p.BN * TC_BK);
   float* img_lo = img_hi + p.BN * TC_BK;
-  for (int i = threadIdx.x; i < p.BN * 8; i += blockDim.x) {
-    const int nl = i % p.BN;              // consecutive threads -> consecutive n: coalesced reads per k
-    const int c16 = i / p.BN;             // 16-byte chunk (4 k values) inside the 128-byte row
-    const int n = tile * p.BN + nl;
-    float hi[4], lo[4];
+  const int nl = blockIdx.z * 32 + (threadIdx.x & 31);   // consecutive threads -> consecutive n: coalesced reads per k
+  const int c16 = threadIdx.x >> 5;                      // 16-byte chunk (4 k values) inside the 128-byte row
+  if (nl >= p.BN) return;
+  const int n = tile * p.BN + nl;
+  float hi[4], lo[4];
+  float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (n < p.n_total) {
+    const int blk = n / p.block_cols, col = n - blk * p.block_cols;
+    const float* src = (seg2 ? p.b2[blk] : p.b1[blk]) + col;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = k0 + c16 * 4 + j;
-      float x = 0.0f;
-      if (n < p.n_total && k < Kseg) {
-        const int blk = n / p.block_cols, col = n - blk * p.block_cols;
-        const float* src = seg2 ? p.b2[blk] : p.b1[blk];
-        x = __ldg(src + (size_t)k * ld + col);
-      }
-      split_tf32(x, hi[j], lo[j]);
+      if (k < Kseg) x[j] = __ldg(src + (size_t)k * ld);
     }
-    const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((c16 ^ (nl & 7)) << 2);   // float index inside the image
-    *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_tf32(x[j], hi[j], lo[j]);
+  const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((c16 ^ (nl & 7)) << 2);   // float index inside the image
+  *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -170,10 +175,21 @@ struct TcParams {
   int BN, stages, chunks1, chunks2;
   int n_total;             // columns of C covered by this launch (batch*N for SHARED_A, else N)
   int tmem_cols;
+  int ring_bytes;          // operand ring, at least as large as the epilogue's [128][BN+4] staging tile
+  long long* trace;        // RGNN_GEMM_TRACE=1: per-CTA clock64 timeline (debug only), else nullptr
 };
+
+// trace slots (clock64 relative to kernel entry): 0 prologue done; 1+3c producer got stage; 2+3c loads landed;
+// 3+3c arrived (c < 8); 32+2c MMA saw full; 33+2c MMA committed (c < 8); 56 epilogue start; 57 epilogue end
+#define TC_TRACE(slot)                                                                          \
+  do {                                                                                          \
+    if (p.trace != nullptr) p.trace[(size_t)cta_lin * 64 + (slot)] = clock64() - t_entry;       \
+  } while (0)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const long long t_entry = clock64();
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   const GemmParams& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN, S = p.stages;
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
   const int stage_bytes = 2 * A_IMG_BYTES + 2 * b_img_bytes;
   // 1024-byte aligned operand ring, then barriers
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.ring_bytes);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accum_bar = smem_u32(bars + 2 * S);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
 
@@ -204,6 +220,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
   const int n_tile = blockIdx.x, n0 = n_tile * BN;
   const int nchunks = p.chunks1 + p.chunks2;
 
+  // A-producer helper: the 8 float4 of chunk c this thread owns (rows tid/8 + 16 i, 16-byte column tid%8)
+  auto load_a_chunk = [&](int c, float4 (&v)[8]) {
+    const bool seg2 = c >= p.chunks1;
+    const int k0 = (seg2 ? c - p.chunks1 : c) * TC_BK;
+    const int Kseg = seg2 ? g.K2 : g.K1;
+    const float* Abase = seg2 ? g.A2 : A1;
+    const int lda = seg2 ? g.lda2 : g.lda1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = tid + i * (TC_PRODUCER_WARPS * 32);
+      const int row = f >> 3, c16 = f & 7;
+      const int grow = m0 + row, gk = k0 + c16 * 4;
+      v[i] = (grow < row_end && gk < Kseg) ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)grow * lda + gk))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float4 va[8];
+  if (warp < TC_PRODUCER_WARPS) load_a_chunk(0, va);   // in flight while barriers / TMEM are set up
+
   if (warp == TC_PRODUCER_WARPS && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, TC_PRODUCER_WARPS * 32 + 1);   // 128 producer arrivals + the B loader's expect_tx arrival
@@ -221,60 +256,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) TC_TRACE(0);
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================== A producers ===========================
+    // Software pipeline: the loads of chunk c+1 are issued before chunk c is split and stored, so the L2
+    // round trip overlaps the conversion (trace r01: serial load->store cost 1450 cycles per chunk).
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % S;
       const uint32_t use = c / S;
+      float4 vn[8];
+      if (c + 1 < nchunks) load_a_chunk(c + 1, vn);
       if (c >= S) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
-      const bool seg2 = c >= p.chunks1;
-      const int k0 = (seg2 ? c - p.chunks1 : c) * TC_BK;
-      const int Kseg = seg2 ? g.K2 : g.K1;
-      const float* Abase = seg2 ? g.A2 : A1;
-      const int lda = seg2 ? g.lda2 : g.lda1;
+      if (tid == 0 && c < 8) TC_TRACE(1 + 3 * c);
       uint8_t* a_hi = ring + (size_t)s * stage_bytes;
       uint8_t* a_lo = a_hi + A_IMG_BYTES;
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {                 // all 8 loads first (memory-level parallelism)
-        const int f = tid + i * (TC_PRODUCER_WARPS * 32);
-        const int row = f >> 3, c16 = f & 7;
-        const int grow = m0 + row, gk = k0 + c16 * 4;
-        v[i] = (grow < row_end && gk < Kseg) ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)grow * lda + gk))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int f = tid + i * (TC_PRODUCER_WARPS * 32);
         const int row = f >> 3, c16 = f & 7;
         float4 hi, lo;
-        split_tf32(v[i].x, hi.x, lo.x); split_tf32(v[i].y, hi.y, lo.y);
-        split_tf32(v[i].z, hi.z, lo.z); split_tf32(v[i].w, hi.w, lo.w);
+        split_tf32(va[i].x, hi.x, lo.x); split_tf32(va[i].y, hi.y, lo.y);
+        split_tf32(va[i].z, hi.z, lo.z); split_tf32(va[i].w, hi.w, lo.w);
         const int off = row * 128 + ((c16 ^ (row & 7)) << 4);
         *reinterpret_cast<float4*>(a_hi + off) = hi;
         *reinterpret_cast<float4*>(a_lo + off) = lo;
       }
       fence_proxy_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(full0 + 8 * s);
+      if (tid == 0 && c < 8) TC_TRACE(3 + 3 * c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) va[i] = vn[i];
     }
     // =========================== epilogue ===========================
+    // TMEM -> registers (thread = row) -> padded smem tile -> row-contiguous reads: bias / activation /
+    // GRU math and 128-bit stores are coalesced along the row (the thread-per-row stores of v1 cost 6000
+    // cycles per tile).  The operand ring is free: accum_bar fires after the last MMA has read it.
     mbar_wait(accum_bar, 0);
+    if (tid == 0) TC_TRACE(56);
     __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
     tc_fence_after_sync();
-    const int r = m0 + warp * 32 + lane;            // TMEM lane == tile row; warp w owns lanes [32w, 32w+32)
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int dgru = (g.epi == EPI_GRU_ZR) ? g.N / 2 : g.N;
-    for (int cb = 0; cb < BN; cb += 16) {
-      float v[16];
-      tmem_ld16(lane_base + cb, v);                 // warp-collective: every lane executes it
-      const int c0 = n0 + cb;
-      if (r >= row_end || c0 >= p.n_total) continue;
+    float* stile = reinterpret_cast<float*>(ring);  // [128][BN + 4]
+    const int lds = BN + 4;
+    {
+      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);   // warp w owns TMEM lanes [32w, 32w+32)
+      float* srow = stile + (size_t)(warp * 32 + lane) * lds;
+      for (int cb = 0; cb < BN; cb += 16) {
+        float v[16];
+        tmem_ld16(lane_base + cb, v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = c0 + q * 4;
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(srow + cb + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    }
+    __syncwarp();                                   // each warp re-reads only the 32 rows it wrote
+    const int dgru = (g.epi == EPI_GRU_ZR) ? g.N / 2 : g.N;
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r = m0 + warp * 32 + rr;
+      if (r >= row_end) break;
+      const float* srow = stile + (size_t)(warp * 32 + rr) * lds;
+      for (int c4 = lane; c4 < BN / 4; c4 += 32) {
+        const int c = n0 + c4 * 4;
         if (c >= p.n_total) break;
-        float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        float4 o = *reinterpret_cast<const float4*>(srow + c4 * 4);
         if (g.bias != nullptr) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + c));
           o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
@@ -301,6 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
         }
       }
     }
+    if (tid == 0) TC_TRACE(57);
   } else if (warp == TC_PRODUCER_WARPS) {
     // =========================== MMA issuer (one thread) ===========================
     if (lane == 0) {
@@ -308,6 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % S;
         mbar_wait(full0 + 8 * s, (c / S) & 1);
+        if (c < 8) TC_TRACE(32 + 2 * c);
         tc_fence_after_sync();
         const uint32_t a_hi = smem_u32(ring + (size_t)s * stage_bytes);
         const uint32_t a_lo = a_hi + A_IMG_BYTES;
@@ -323,6 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
           umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1);
         }
         umma_commit(empty0 + 8 * s);                // stage reusable once these MMAs have read it
+        if (c < 8) TC_TRACE(33 + 2 * c);
       }
       umma_commit(accum_bar);                       // accumulator complete -> epilogue
     }
@@ -424,21 +471,44 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
       RGNN_REQUIRE(q.b1[j] != nullptr && (g.K2 == 0 || q.b2[j] != nullptr), "gemm: weight pointer %d is NULL", j);
     }
     q.out = static_cast<float*>(pack_ws) + (size_t)zz * p.packed_stride;
-    pack_b_kernel<<<dim3(nchunks, n_tiles), 256, 0, stream>>>(q);
+    pack_b_kernel<<<dim3(nchunks, n_tiles, (p.BN + 31) / 32), 256, 0, stream>>>(q);
     RGNN_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
 
-  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
+  const size_t epi_tile = (size_t)TC_BM * (p.BN + 4) * sizeof(float);
+  p.ring_bytes = (int)align_up(std::max((size_t)p.stages * stage_bytes, epi_tile), 1024);
+  const size_t smem = 1024 + (size_t)p.ring_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     attr_smem = 220 * 1024;
   }
   dim3 grid(n_tiles, (rows + TC_BM - 1) / TC_BM, gz);
+  static const bool trace_on = getenv("RGNN_GEMM_TRACE") != nullptr;
+  const size_t n_ctas = (size_t)grid.x * grid.y * grid.z;
+  p.trace = nullptr;
+  if (trace_on) {   // debug only: synchronous, prints one timeline summary per launch to stderr
+    RGNN_CHECK_CUDA(cudaMalloc(&p.trace, n_ctas * 64 * sizeof(long long)));
+    RGNN_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, n_ctas * 64 * sizeof(long long), stream));
+  }
   gemm_tcgen05_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  if (trace_on) {
+    std::vector<long long> h(n_ctas * 64);
+    RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
+    RGNN_CHECK_CUDA(cudaMemcpy(h.data(), p.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    fprintf(stderr, "[gemm trace] M=%d N=%d K=%d+%d BN=%d stages=%d ctas=%zu chunks=%d\n", g.M, p.n_total, g.K1, g.K2, p.BN, p.stages, n_ctas, nchunks);
+    const size_t picks[3] = {0, n_ctas / 2, n_ctas - 1};
+    for (size_t pi = 0; pi < 3; ++pi) {
+      const long long* t = h.data() + picks[pi] * 64;
+      fprintf(stderr, "  cta %zu: prologue %lld |", picks[pi], t[0]);
+      for (int c = 0; c < 8 && c < nchunks; ++c) fprintf(stderr, " c%d got %lld landed %lld arrived %lld mma_full %lld mma_commit %lld |", c, t[1 + 3 * c], t[2 + 3 * c], t[3 + 3 * c], t[32 + 2 * c], t[33 + 2 * c]);
+      fprintf(stderr, " epi %lld..%lld\n", t[56], t[57]);
+    }
+  }
   return RGNN_OK;
 }
 
