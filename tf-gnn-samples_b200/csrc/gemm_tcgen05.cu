@@ -28,12 +28,32 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                    // fp32 elements per 128-byte swizzle row
-constexpr int TC_PRODUCER_WARPS = 4;
+constexpr int TC_GROUPS = 2;                 // producer groups alternate K chunks (see the producer loop)
+constexpr int TC_GROUP_WARPS = 4;            // one group covers the 128-row tile: 4 warps x 32 rows of TMEM lanes
+constexpr int TC_PRODUCER_WARPS = TC_GROUPS * TC_GROUP_WARPS;
+constexpr int TC_GROUP_THREADS = 32 * TC_GROUP_WARPS;
 constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + 2);   // + MMA warp + B-loader warp
 constexpr int A_IMG_BYTES = TC_BM * 128;     // 16 KB
 constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// Explicit shared-space accesses on 32-bit shared addresses.  (Going through a generic pointer that was
+// rounded up via uintptr_t made ptxas emit generic ST.E.128 + MEMBAR.ALL.CTA in front of the proxy fence,
+// which waited on the prefetched global loads and serialised the whole pipeline -- r01 trace.)
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -195,11 +215,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
   const int BN = p.BN, S = p.stages;
   const int b_img_bytes = BN * 128;
   const int stage_bytes = 2 * A_IMG_BYTES + 2 * b_img_bytes;
-  // 1024-byte aligned operand ring, then barriers
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.ring_bytes);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accum_bar = smem_u32(bars + 2 * S);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  // 1024-byte aligned operand ring (32-bit shared addresses), then barriers
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t ring = (smem_base + 1023u) & ~1023u;
+  const uint32_t full0 = ring + (uint32_t)p.ring_bytes, empty0 = full0 + 8 * S, accum_bar = full0 + 16 * S;
+  const uint32_t tmem_slot = accum_bar + 8;
 
   // ---- operands of this CTA ----
   const int z = blockIdx.z;
@@ -220,7 +240,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
   const int n_tile = blockIdx.x, n0 = n_tile * BN;
   const int nchunks = p.chunks1 + p.chunks2;
 
-  // A-producer helper: the 8 float4 of chunk c this thread owns (rows tid/8 + 16 i, 16-byte column tid%8)
+  // A-producer helper: the 8 float4 of chunk c this thread owns (rows ptid/8 + 16 i, 16-byte column ptid%8)
+  const int group = warp / TC_GROUP_WARPS;          // producer group (meaningful for warps < TC_PRODUCER_WARPS)
+  const int ptid = tid % TC_GROUP_THREADS;          // thread index inside the group
   auto load_a_chunk = [&](int c, float4 (&v)[8]) {
     const bool seg2 = c >= p.chunks1;
     const int k0 = (seg2 ? c - p.chunks1 : c) * TC_BK;
@@ -229,7 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
     const int lda = seg2 ? g.lda2 : g.lda1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int f = tid + i * (TC_PRODUCER_WARPS * 32);
+      const int f = ptid + i * TC_GROUP_THREADS;
       const int row = f >> 3, c16 = f & 7;
       const int grow = m0 + row, gk = k0 + c16 * 4;
       v[i] = (grow < row_end && gk < Kseg) ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)grow * lda + gk))
@@ -237,11 +259,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
     }
   };
   float4 va[8];
-  if (warp < TC_PRODUCER_WARPS) load_a_chunk(0, va);   // in flight while barriers / TMEM are set up
+  if (warp < TC_PRODUCER_WARPS && group < nchunks) load_a_chunk(group, va);   // in flight while barriers / TMEM are set up
 
   if (warp == TC_PRODUCER_WARPS && lane == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full0 + 8 * s, TC_PRODUCER_WARPS * 32 + 1);   // 128 producer arrivals + the B loader's expect_tx arrival
+      mbar_init(full0 + 8 * s, TC_GROUP_THREADS + 1);         // 128 producer arrivals + the B loader's expect_tx arrival
       mbar_init(empty0 + 8 * s, 1);                           // one tcgen05.commit
     }
     mbar_init(accum_bar, 1);
@@ -249,44 +271,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
   }
   __syncwarp();
   if (warp == TC_PRODUCER_WARPS) {                  // TMEM allocation by the MMA warp (it also frees it)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds32(tmem_slot);
   if (tid == 0) TC_TRACE(0);
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================== A producers ===========================
-    // Software pipeline: the loads of chunk c+1 are issued before chunk c is split and stored, so the L2
-    // round trip overlaps the conversion (trace r01: serial load->store cost 1450 cycles per chunk).
-    for (int c = 0; c < nchunks; ++c) {
+    // Two producer groups alternate chunks (group g owns chunks g, g+2, ...).  A thread issues the loads of
+    // its NEXT chunk right after publishing the current one, so they fly while the other group converts:
+    // fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the membar waits for the issuing
+    // thread's outstanding loads -- prefetching inside one group would be serialised by it (r01 trace).
+    for (int c = group; c < nchunks; c += TC_GROUPS) {
       const int s = c % S;
       const uint32_t use = c / S;
-      float4 vn[8];
-      if (c + 1 < nchunks) load_a_chunk(c + 1, vn);
       if (c >= S) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
       if (tid == 0 && c < 8) TC_TRACE(1 + 3 * c);
-      uint8_t* a_hi = ring + (size_t)s * stage_bytes;
-      uint8_t* a_lo = a_hi + A_IMG_BYTES;
+      const uint32_t a_hi = ring + (uint32_t)(s * stage_bytes);
+      const uint32_t a_lo = a_hi + A_IMG_BYTES;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int f = tid + i * (TC_PRODUCER_WARPS * 32);
+        const int f = ptid + i * TC_GROUP_THREADS;
         const int row = f >> 3, c16 = f & 7;
         float4 hi, lo;
         split_tf32(va[i].x, hi.x, lo.x); split_tf32(va[i].y, hi.y, lo.y);
         split_tf32(va[i].z, hi.z, lo.z); split_tf32(va[i].w, hi.w, lo.w);
-        const int off = row * 128 + ((c16 ^ (row & 7)) << 4);
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = lo;
+        const uint32_t off = (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4));
+        sts128(a_hi + off, hi);
+        sts128(a_lo + off, lo);
       }
       fence_proxy_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(full0 + 8 * s);
       if (tid == 0 && c < 8) TC_TRACE(3 + 3 * c);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) va[i] = vn[i];
+      if (c + TC_GROUPS < nchunks) load_a_chunk(c + TC_GROUPS, va);
     }
     // =========================== epilogue ===========================
     // TMEM -> registers (thread = row) -> padded smem tile -> row-contiguous reads: bias / activation /
@@ -296,29 +317,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
     if (tid == 0) TC_TRACE(56);
     __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
     tc_fence_after_sync();
-    float* stile = reinterpret_cast<float*>(ring);  // [128][BN + 4]
-    const int lds = BN + 4;
+    const uint32_t stile = ring;                    // [128][BN + 4] fp32
+    const uint32_t lds = (uint32_t)(BN + 4) * 4;    // row pitch in bytes
     {
-      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);   // warp w owns TMEM lanes [32w, 32w+32)
-      float* srow = stile + (size_t)(warp * 32 + lane) * lds;
-      for (int cb = 0; cb < BN; cb += 16) {
+      const int quarter = warp % TC_GROUP_WARPS;    // a warp may only touch TMEM lanes [32*(warp%4), +32)
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t srow = stile + (uint32_t)(quarter * 32 + lane) * lds;
+      for (int cb = group * 16; cb < BN; cb += 16 * TC_GROUPS) {   // the two groups split the 16-column blocks
         float v[16];
         tmem_ld16(lane_base + cb, v);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(srow + cb + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          sts128(srow + (uint32_t)(cb + q * 4) * 4, make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]));
       }
     }
-    __syncwarp();                                   // each warp re-reads only the 32 rows it wrote
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");   // producer warps only
     const int dgru = (g.epi == EPI_GRU_ZR) ? g.N / 2 : g.N;
-    for (int rr = 0; rr < 32; ++rr) {
-      const int r = m0 + warp * 32 + rr;
+    constexpr int ROWS_PER_WARP = TC_BM / TC_PRODUCER_WARPS;
+    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+      const int r = m0 + warp * ROWS_PER_WARP + rr;
       if (r >= row_end) break;
-      const float* srow = stile + (size_t)(warp * 32 + rr) * lds;
+      const uint32_t srow = stile + (uint32_t)(warp * ROWS_PER_WARP + rr) * lds;
       for (int c4 = lane; c4 < BN / 4; c4 += 32) {
         const int c = n0 + c4 * 4;
         if (c >= p.n_total) break;
-        float4 o = *reinterpret_cast<const float4*>(srow + c4 * 4);
+        float4 o = lds128(srow + (uint32_t)c4 * 16);
         if (g.bias != nullptr) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + c));
           o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
@@ -355,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
         mbar_wait(full0 + 8 * s, (c / S) & 1);
         if (c < 8) TC_TRACE(32 + 2 * c);
         tc_fence_after_sync();
-        const uint32_t a_hi = smem_u32(ring + (size_t)s * stage_bytes);
+        const uint32_t a_hi = ring + (uint32_t)(s * stage_bytes);
         const uint32_t a_lo = a_hi + A_IMG_BYTES;
         const uint32_t b_hi = a_lo + A_IMG_BYTES;
         const uint32_t b_lo = b_hi + b_img_bytes;
@@ -381,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % S;
         if (c >= S) mbar_wait(empty0 + 8 * s, ((c / S) - 1) & 1);
-        const uint32_t b_hi = smem_u32(ring + (size_t)s * stage_bytes + 2 * A_IMG_BYTES);
+        const uint32_t b_hi = ring + (uint32_t)(s * stage_bytes + 2 * A_IMG_BYTES);
         mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);
         bulk_copy_g2s(b_hi, src_tile + (size_t)c * 2 * (BN * TC_BK), 2 * b_img_bytes, full0 + 8 * s);   // hi and lo are adjacent
       }

@@ -63,15 +63,18 @@ __device__ __forceinline__ void warp_layer_norm(float4 (&x)[NV], const bool (&ok
 }
 
 // NV float4 per lane (the warp covers 128*NV columns starting at blockIdx.y * 128*NV); MODE = MsgMode;
-// MAXAGG = tf.unsorted_segment_max.  Layer-norm epilogues need the whole row in one warp (gridDim.y == 1).
-template <int NV, int MODE, bool MAXAGG>
+// MAXAGG = tf.unsorted_segment_max; SCALED = per-message 1/(c+1e-7).  Layer-norm epilogues need the whole row
+// in one warp (gridDim.y == 1).  The edge loop is lean on purpose (profiles/r01_seg_reduce_v2.txt showed the
+// previous version issue-bound at 34 warp-instructions per 512-byte row): one 32-bit row id and one scale are
+// broadcast per edge, rows are fetched in unpredicated groups of GROUP, remainder handled separately.
+template <int NV, int MODE, bool MAXAGG, bool SCALED>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const __grid_constant__ SegParams p) {
+  constexpr int GROUP = (NV <= 2) ? 8 : 4;   // rows in flight per warp
   const int lane = threadIdx.x & 31;
   const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (v >= p.V) return;
   const int col0 = blockIdx.y * (128 * NV) + lane * 4;
   const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
-  const bool scaled = p.num_incoming != nullptr;
   const int act_msg = p.act_msg;
 
   bool ok[NV];
@@ -86,65 +89,101 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const 
 #pragma unroll
   for (int k = 0; k < NV; ++k) { m0[k] = f4(1.0f); m1[k] = f4(0.0f); }
   const float* tbase = p.table + col0;
+  const long row_stride = p.stride_type;            // row id = e_idx * rows_per_idx + type (see SegParams)
+  const int rows_per_idx = (int)(p.stride_idx / (p.stride_type > 0 ? p.stride_type : p.stride_idx));
+  const bool typed_rows = p.stride_type > 0;
+
+  // consume one gathered row (registers r) of message (scale sc, type ty)
+  auto consume = [&](const float4 (&r)[NV], float sc, int ty) {
+    if (MODE != MSG_LINEAR) {
+      if (ty != cur_type) {   // warp-uniform: new (v, type) run
+        cur_type = ty;
+        const float* mrow = p.mod_table + (size_t)v * p.mod_stride_node + (size_t)ty * p.mod_stride_type + col0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+          if (ok[k]) {
+            m0[k] = ldg4(mrow + k * 128);
+            if (MODE == MSG_FILM) m1[k] = ldg4(mrow + p.D + k * 128);
+          }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (ok[k]) {
+        float4 m = r[k];
+        if (MODE == MSG_LINEAR && !MAXAGG) {
+          if (act_msg == RGNN_ACT_LINEAR) {          // hot path: acc += s * t, one FMA (or add) per element
+            if (SCALED) {
+              acc[k].x = fmaf(m.x, sc, acc[k].x); acc[k].y = fmaf(m.y, sc, acc[k].y);
+              acc[k].z = fmaf(m.z, sc, acc[k].z); acc[k].w = fmaf(m.w, sc, acc[k].w);
+            } else {
+              acc[k] = add4(acc[k], m);
+            }
+            continue;
+          }
+        }
+        if (MODE == MSG_LINEAR) {
+          if (SCALED) m = mul4(m, sc);
+        } else if (MODE == MSG_FILM) {
+          if (SCALED) m = mul4(m, sc);
+          m = fma4(m0[k], m, m1[k]);
+        } else {
+          m = add4(m, m0[k]);
+          if (SCALED) m = mul4(m, sc);
+        }
+        m = act4(m, act_msg);
+        acc[k] = MAXAGG ? max4(acc[k], m) : add4(acc[k], m);
+      }
+  };
 
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int n = min(32, end - e0);
-    int my_type = 0;
+    int my_type = 0, my_row = 0;
     float my_scale = 1.0f;
-    long my_off = 0;
     if (lane < n) {
       my_type = __ldg(p.e_type + e0 + lane);
-      my_off = (long)__ldg(p.e_idx + e0 + lane) * p.stride_idx + (long)my_type * p.stride_type;
-      if (scaled)   // 1.0f / (c + SMALL_NUMBER) evaluated in fp32 like the reference (rgcn.py:104)
+      const int idx = __ldg(p.e_idx + e0 + lane);
+      my_row = typed_rows ? idx * rows_per_idx + my_type : idx;
+      if (SCALED)   // 1.0f / (c + SMALL_NUMBER) evaluated in fp32 like the reference (rgcn.py:104)
         my_scale = 1.0f / (__ldg(p.num_incoming + (size_t)my_type * p.V + v) + 1e-7f);
     }
-    for (int j = 0; j < n; j += UNROLL) {
-      float4 r[UNROLL][NV];
+    const long stride = typed_rows ? row_stride : p.stride_idx;
+    int j = 0;
+    for (; j + GROUP <= n; j += GROUP) {             // full groups: GROUP rows in flight, no predicates
+      float4 r[GROUP][NV];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
+      for (int u = 0; u < GROUP; ++u) {
+        const int row = __shfl_sync(0xffffffffu, my_row, j + u);
+        const float* src = tbase + (long)row * stride;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+          if (ok[k]) r[u][k] = ldg4(src + k * 128);
+      }
+#pragma unroll
+      for (int u = 0; u < GROUP; ++u) {
+        const float sc = SCALED ? __shfl_sync(0xffffffffu, my_scale, j + u) : 1.0f;
+        const int ty = (MODE != MSG_LINEAR) ? __shfl_sync(0xffffffffu, my_type, j + u) : 0;
+        consume(r[u], sc, ty);
+      }
+    }
+    if (j < n) {                                     // remainder (< GROUP rows): predicated loads, same order
+      float4 r[GROUP][NV];
+#pragma unroll
+      for (int u = 0; u < GROUP; ++u) {
         if (j + u < n) {
-          const long off = __shfl_sync(0xffffffffu, my_off, j + u);
+          const int row = __shfl_sync(0xffffffffu, my_row, j + u);
+          const float* src = tbase + (long)row * stride;
 #pragma unroll
           for (int k = 0; k < NV; ++k)
-            if (ok[k]) r[u][k] = ldg4(tbase + off + k * 128);
+            if (ok[k]) r[u][k] = ldg4(src + k * 128);
         }
       }
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
+      for (int u = 0; u < GROUP; ++u) {
         if (j + u < n) {
-          const float sc = __shfl_sync(0xffffffffu, my_scale, j + u);
-          if (MODE != MSG_LINEAR) {
-            const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
-            if (ty != cur_type) {   // warp-uniform: new (v, type) run
-              cur_type = ty;
-              const float* mrow = p.mod_table + (size_t)v * p.mod_stride_node + (size_t)ty * p.mod_stride_type + col0;
-#pragma unroll
-              for (int k = 0; k < NV; ++k)
-                if (ok[k]) {
-                  m0[k] = ldg4(mrow + k * 128);
-                  if (MODE == MSG_FILM) m1[k] = ldg4(mrow + p.D + k * 128);
-                }
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < NV; ++k)
-            if (ok[k]) {
-              float4 m = r[u][k];
-              if (MODE == MSG_LINEAR) {
-                if (!MAXAGG && act_msg == RGNN_ACT_LINEAR) {   // hot path: acc += s * t as one FMA per element
-                  acc[k].x = fmaf(m.x, sc, acc[k].x); acc[k].y = fmaf(m.y, sc, acc[k].y);
-                  acc[k].z = fmaf(m.z, sc, acc[k].z); acc[k].w = fmaf(m.w, sc, acc[k].w);
-                  continue;
-                }
-                m = mul4(m, sc);
-              } else if (MODE == MSG_FILM) {
-                m = fma4(m0[k], mul4(m, sc), m1[k]);
-              } else {
-                m = mul4(add4(m, m0[k]), sc);
-              }
-              m = act4(m, act_msg);
-              acc[k] = MAXAGG ? max4(acc[k], m) : add4(acc[k], m);
-            }
+          const float sc = SCALED ? __shfl_sync(0xffffffffu, my_scale, j + u) : 1.0f;
+          const int ty = (MODE != MSG_LINEAR) ? __shfl_sync(0xffffffffu, my_type, j + u) : 0;
+          consume(r[u], sc, ty);
         }
       }
     }
@@ -319,10 +358,15 @@ inline int nv_for(int D) { return (D + 127) / 128; }
 
 }  // namespace
 
+template <int NV, int MODE, bool MAXAGG>
+static void launch_seg_scaled(const SegParams& p, dim3 grid, cudaStream_t stream) {
+  if (p.num_incoming != nullptr) seg_reduce_kernel<NV, MODE, MAXAGG, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  else seg_reduce_kernel<NV, MODE, MAXAGG, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+}
 template <int NV, int MODE>
 static void launch_seg_variant(const SegParams& p, dim3 grid, cudaStream_t stream) {
-  if (p.agg == RGNN_AGG_MAX) seg_reduce_kernel<NV, MODE, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
-  else seg_reduce_kernel<NV, MODE, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  if (p.agg == RGNN_AGG_MAX) launch_seg_scaled<NV, MODE, true>(p, grid, stream);
+  else launch_seg_scaled<NV, MODE, false>(p, grid, stream);
 }
 template <int NV>
 static void launch_seg_nv(const SegParams& p, dim3 grid, cudaStream_t stream) {
@@ -340,6 +384,8 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
                "segment reduce: rows must be 16-byte aligned");
   if (p.V == 0) return RGNN_OK;
   const unsigned gx = (p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  RGNN_REQUIRE(p.stride_type == 0 || (p.stride_idx % p.stride_type) == 0, "segment reduce: stride_idx must be a multiple of stride_type");
+  RGNN_REQUIRE((long)p.V * (p.stride_type > 0 ? p.stride_idx / p.stride_type : 1) < (1L << 31), "segment reduce: table has more than 2^31 rows");
   if (p.ln_gamma != nullptr) {   // the layer-norm epilogue needs the whole row inside one warp
     if (p.D > RGNN_MAX_STATE_DIM) {
       set_error("segment reduce: layer-norm epilogue supports state dim <= %d, got %d", RGNN_MAX_STATE_DIM, p.D);
@@ -352,9 +398,10 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
       case 3: launch_seg_nv<3>(p, grid, stream); break;
       default: launch_seg_nv<4>(p, grid, stream); break;
     }
-  } else {                       // otherwise one warp per 128-column slice of a target row: more rows in flight
-    const dim3 grid(gx, (p.D + 127) / 128);
-    launch_seg_nv<1>(p, grid, stream);
+  } else {                       // otherwise one warp per <= 256-column slice of a target row
+    RGNN_REQUIRE(p.stride_type == 0 || (p.stride_idx % p.stride_type) == 0, "segment reduce: stride_idx must be a multiple of stride_type");
+    if (p.D <= 128) launch_seg_nv<1>(p, dim3(gx, 1), stream);
+    else launch_seg_nv<2>(p, dim3(gx, (p.D + 255) / 256), stream);
   }
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
