@@ -220,6 +220,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    G.set_weight_cache(True)   # static weights: the GEMM's pre-swizzled weight images are built once, not per step
     batch, h0, layer_weights = make_inputs(seed=rank)        # weak scaling: every rank owns its own batch
     V, M, L = batch.num_nodes, batch.num_edges, len(batch.adjacency_lists)
     ws = [W.to_torch(w, dev) for w in layer_weights]
@@ -365,6 +366,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "l2": "flushed between timed steps (256 MiB write, untimed)",
                    "step": "3 x sparse_rgcn_layer replayed as one CUDA graph (%d kernels)" % kernels_per_step,
                    "parallelism": "independent batch per rank (graph-boundary sharding, no collective)",
+                   "weights": "static: packed TF32 hi/lo weight images cached across steps (rgnn_set_weight_cache)",
                    "warm_l2_ms_per_step": warm_ms, "per_layer_edges_per_s": M / (layer_ms * 1e-3)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "one RGCN layer = gemm_tf32x3 (node transform) + seg_reduce (edge stage)",

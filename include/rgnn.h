@@ -94,6 +94,14 @@ RGNN_API int64_t rgnn_plan_num_edges(const rgnn_plan_t* plan);       /* M = sum_
 RGNN_API int rgnn_plan_export(const rgnn_plan_t* plan, int32_t* seg_off, int32_t* e_src, int32_t* e_type,
                      int32_t* e_orig, void* stream);
 
+/* Static-weight mode (inference / benchmarking), off by default.  The tensor-core GEMM consumes the
+ * weights as pre-swizzled TF32 hi/lo shared-memory images; normally they are rebuilt from the caller's
+ * kernels on every forward.  With the cache on, images are built once per distinct (weight pointers,
+ * shape, tiling) and reused; the caller must call rgnn_weight_cache_clear() after changing cached weights
+ * in place.  A cache miss inside CUDA-graph capture is an error (run the layer once eagerly first). */
+RGNN_API int rgnn_set_weight_cache(int enable);
+RGNN_API int rgnn_weight_cache_clear(void);
+
 /* Upper bound of the scratch a forward of `layer_kind` needs.  mlp_layers = number of kernels
  * in the widest edge/aggregation MLP (0 if none). */
 RGNN_API size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, int32_t d_in, int32_t d_out,

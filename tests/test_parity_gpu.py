@@ -250,3 +250,31 @@ def test_error_behaviour(cuda_device):
         sparse_rgcn_layer(h.cpu(), adj, indeg, 64, weights=w)
     with pytest.raises(RgnnError):   # num_timesteps > 1 needs state_dim == D (rgcn.py docstring)
         sparse_rgcn_layer(h, adj, indeg, 32, num_timesteps=2, weights=W.to_torch(W.rgcn_weights(4, 64, 32), cuda_device))
+
+
+# ---------------------------------------------------------------- static-weight cache --------------------
+def test_weight_cache_tracks_in_place_updates(cuda_device):
+    import torch
+    import tf_gnn_samples_b200 as G
+    b = batching.ppi_like_batch(num_nodes=500, num_links=6000, seed=5)
+    h = node_states(b.num_nodes, 128)
+    w = W.rgcn_weights(3, 128, 128, seed=77)
+    wt = W.to_torch(w, cuda_device)
+    ht = torch.as_tensor(h).to(cuda_device)
+    cnt = torch.as_tensor(b.type_to_num_incoming_edges).to(cuda_device)
+    plan = GraphPlan(b.adjacency_lists, b.num_nodes, device=cuda_device)
+    G.set_weight_cache(True)
+    try:
+        first = sparse_rgcn_layer(ht, plan, cnt, 128, activation_function="tanh", weights=wt).cpu().numpy()
+        again = sparse_rgcn_layer(ht, plan, cnt, 128, activation_function="tanh", weights=wt).cpu().numpy()
+        assert np.array_equal(first, again)                          # second call served from the cached images
+        assert_parity(first, R.sparse_rgcn_layer(h, b.adjacency_lists, b.type_to_num_incoming_edges, 128,
+                                                 activation_function="tanh", weights=w), "cached weights")
+        for k in wt["edge_weights"]:
+            k.mul_(0.5)                                              # in-place update bumps Tensor._version
+        w2 = {"edge_weights": [0.5 * k for k in w["edge_weights"]]}
+        changed = sparse_rgcn_layer(ht, plan, cnt, 128, activation_function="tanh", weights=wt).cpu().numpy()
+        assert_parity(changed, R.sparse_rgcn_layer(h, b.adjacency_lists, b.type_to_num_incoming_edges, 128,
+                                                   activation_function="tanh", weights=w2), "cache flushed on update")
+    finally:
+        G.set_weight_cache(False)

@@ -6,7 +6,7 @@ anywhere, calling them requires the CUDA library and a GPU and fails loudly othe
 """
 from .utils import (SMALL_NUMBER, BIG_NUMBER, get_activation, get_aggregation_function,  # noqa: F401
                     get_gated_unit)
-from .engine import GraphPlan, RgnnError, launch_count  # noqa: F401
+from .engine import GraphPlan, RgnnError, launch_count, set_weight_cache, weight_cache_clear  # noqa: F401
 from .gnns import (sparse_rgcn_layer, sparse_ggnn_layer, sparse_rgat_layer, sparse_rgin_layer,  # noqa: F401
                    sparse_gnn_edge_mlp_layer, sparse_gnn_film_layer)
 

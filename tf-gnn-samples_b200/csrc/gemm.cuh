@@ -52,6 +52,11 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream);
 size_t gemm_tc_pack_bytes(const GemmParams& p);
 int launch_gemm_tcgen05(const GemmParams& p, void* pack_ws, size_t pack_ws_bytes, cudaStream_t stream);
 
+// Optional cache of the packed weight images (static weights).  See rgnn_set_weight_cache in include/rgnn.h.
+void gemm_weight_cache_enable(bool on);
+void gemm_weight_cache_clear();
+bool gemm_weight_cache_enabled();
+
 // true unless the environment says RGNN_GEMM_IMPL=mma
 bool gemm_use_tcgen05();
 

@@ -20,6 +20,7 @@
 
 #include <stdlib.h>
 #include <vector>
+#include <mutex>
 #include <algorithm>
 
 namespace rgnn {
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
       const int s = c % S;
       const uint32_t use = c / S;
       if (c >= S) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
-      if (tid == 0 && c < 8) TC_TRACE(1 + 3 * c);
+      if (ptid == 0 && c < 8) TC_TRACE(1 + 3 * c);
       const uint32_t a_hi = ring + (uint32_t)(s * stage_bytes);
       const uint32_t a_lo = a_hi + A_IMG_BYTES;
 #pragma unroll
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
       }
       fence_proxy_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(full0 + 8 * s);
-      if (tid == 0 && c < 8) TC_TRACE(3 + 3 * c);
+      if (ptid == 0 && c < 8) TC_TRACE(3 + 3 * c);
       if (c + TC_GROUPS < nchunks) load_a_chunk(c + TC_GROUPS, va);
     }
     // =========================== epilogue ===========================
@@ -331,7 +332,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
           sts128(srow + (uint32_t)(cb + q * 4) * 4, make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]));
       }
     }
+    if (tid == 0) TC_TRACE(58);
     asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");   // producer warps only
+    if (tid == 0) TC_TRACE(59);
     const int dgru = (g.epi == EPI_GRU_ZR) ? g.N / 2 : g.N;
     constexpr int ROWS_PER_WARP = TC_BM / TC_PRODUCER_WARPS;
     for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
@@ -405,6 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
         const int s = c % S;
         if (c >= S) mbar_wait(empty0 + 8 * s, ((c / S) - 1) & 1);
         const uint32_t b_hi = ring + (uint32_t)(s * stage_bytes + 2 * A_IMG_BYTES);
+        if (c < 8) TC_TRACE(2 + 3 * c);
         mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);
         bulk_copy_g2s(b_hi, src_tile + (size_t)c * 2 * (BN * TC_BK), 2 * b_img_bytes, full0 + 8 * s);   // hi and lo are adjacent
       }
@@ -435,7 +439,44 @@ int pick_bn(long m_tiles, int n_total, int gz) {
 
 }  // namespace
 
+// ---- optional cache of packed weight images (static weights: inference / benchmarking) ----------------
+// Off by default.  Keyed by every input of the packing (weight pointers, leading dims, K/N, batching, BN);
+// the caller promises not to modify cached weights in place without calling rgnn_weight_cache_clear().
+struct PackKey {
+  uint64_t h[4];
+  bool operator==(const PackKey& o) const { return h[0] == o.h[0] && h[1] == o.h[1] && h[2] == o.h[2] && h[3] == o.h[3]; }
+};
+struct PackEntry { PackKey key; float* images; size_t bytes; };
+static std::vector<PackEntry> g_pack_cache;
+static std::mutex g_pack_mutex;
+static bool g_pack_cache_on = false;
+
+static inline void mix(uint64_t& h, uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); }
+static PackKey make_pack_key(const GemmParams& g, int BN, int device) {
+  PackKey k = {{0x1234, 0x5678, 0x9abc, (uint64_t)device}};
+  const int nb = (g.batch_mode == BATCH_NONE) ? 1 : g.batch;
+  for (int j = 0; j < nb; ++j) {
+    const uint64_t a = (uint64_t)(g.batch_mode == BATCH_NONE ? g.B1 : g.bptr[j]);
+    const uint64_t b = (uint64_t)(g.batch_mode == BATCH_NONE ? g.B2 : g.bptr2[j]);
+    mix(k.h[j & 1], a); mix(k.h[2], b); mix(k.h[3], a * 31 + b + j);
+  }
+  mix(k.h[0], ((uint64_t)g.K1 << 32) | (uint32_t)g.K2);
+  mix(k.h[1], ((uint64_t)g.N << 32) | (uint32_t)BN);
+  mix(k.h[2], ((uint64_t)g.ldb1 << 32) | (uint32_t)g.ldb2);
+  mix(k.h[3], ((uint64_t)g.batch_mode << 32) | (uint32_t)g.batch);
+  return k;
+}
+
+void gemm_weight_cache_enable(bool on) { std::lock_guard<std::mutex> l(g_pack_mutex); g_pack_cache_on = on; }
+void gemm_weight_cache_clear() {
+  std::lock_guard<std::mutex> l(g_pack_mutex);
+  for (auto& e : g_pack_cache) cudaFree(e.images);
+  g_pack_cache.clear();
+}
+bool gemm_weight_cache_enabled() { return g_pack_cache_on; }
+
 size_t gemm_tc_pack_bytes(const GemmParams& g) {
+  if (g_pack_cache_on) return 1024;   // images live in the cache, the caller's scratch is not used
   const int chunks = (g.K1 + TC_BK - 1) / TC_BK + (g.K2 + TC_BK - 1) / TC_BK;
   const int n_total = (g.batch_mode == BATCH_SHARED_A) ? g.batch * g.N : g.N;
   const int gz = (g.batch_mode == BATCH_ROW_RANGES || g.batch_mode == BATCH_COL_BLOCKS) ? g.batch : 1;
@@ -454,10 +495,6 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   RGNN_REQUIRE(g.bias == nullptr || aligned16(g.bias), "gemm: bias must be 16-byte aligned");
   const int rows = (g.batch_mode == BATCH_ROW_RANGES) ? g.max_rows : g.M;
   if (rows <= 0) return RGNN_OK;
-  const size_t need = gemm_tc_pack_bytes(g);
-  RGNN_REQUIRE(pack_ws != nullptr && pack_ws_bytes >= need && (reinterpret_cast<uintptr_t>(pack_ws) & 15u) == 0,
-               "gemm: weight-image workspace too small (%zu < %zu)", pack_ws_bytes, need);
-
   TcParams p;
   p.g = g;
   p.chunks1 = (g.K1 + TC_BK - 1) / TC_BK;
@@ -473,11 +510,33 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   if (p.stages > nchunks) p.stages = nchunks;
   if (p.stages < 1) p.stages = 1;
   p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
-  p.packed = static_cast<const float*>(pack_ws);
   p.packed_stride = (size_t)n_tiles * nchunks * 2 * p.BN * TC_BK;
+  const size_t need = align_up(p.packed_stride * sizeof(float) * gz, 1024);
+  bool need_pack = true;
+  if (g_pack_cache_on) {
+    int device = 0;
+    cudaGetDevice(&device);
+    const PackKey key = make_pack_key(g, p.BN, device);
+    std::lock_guard<std::mutex> l(g_pack_mutex);
+    float* images = nullptr;
+    for (auto& e : g_pack_cache)
+      if (e.key == key && e.bytes == need) { images = e.images; need_pack = false; break; }
+    if (images == nullptr) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cap);
+      RGNN_REQUIRE(cap == cudaStreamCaptureStatusNone, "gemm: weight cache miss during CUDA-graph capture (run the layer once eagerly first)");
+      RGNN_CHECK_CUDA(cudaMalloc(&images, need));
+      g_pack_cache.push_back({key, images, need});
+    }
+    pack_ws = images;
+  } else {
+    RGNN_REQUIRE(pack_ws != nullptr && pack_ws_bytes >= need && (reinterpret_cast<uintptr_t>(pack_ws) & 15u) == 0,
+                 "gemm: weight-image workspace too small (%zu < %zu)", pack_ws_bytes, need);
+  }
+  p.packed = static_cast<const float*>(pack_ws);
 
   // ---- pack the weights into shared-memory images ----
-  for (int zz = 0; zz < gz; ++zz) {
+  for (int zz = 0; need_pack && zz < gz; ++zz) {
     PackParams q;
     q.ldb1 = g.ldb1; q.ldb2 = g.ldb2; q.K1 = g.K1; q.K2 = g.K2;
     q.BN = p.BN; q.chunks1 = p.chunks1; q.chunks2 = p.chunks2;
@@ -528,8 +587,8 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
     for (size_t pi = 0; pi < 3; ++pi) {
       const long long* t = h.data() + picks[pi] * 64;
       fprintf(stderr, "  cta %zu: prologue %lld |", picks[pi], t[0]);
-      for (int c = 0; c < 8 && c < nchunks; ++c) fprintf(stderr, " c%d got %lld landed %lld arrived %lld mma_full %lld mma_commit %lld |", c, t[1 + 3 * c], t[2 + 3 * c], t[3 + 3 * c], t[32 + 2 * c], t[33 + 2 * c]);
-      fprintf(stderr, " epi %lld..%lld\n", t[56], t[57]);
+      for (int c = 0; c < 8 && c < nchunks; ++c) fprintf(stderr, " c%d got %lld Bissue %lld arrived %lld mma_full %lld mma_commit %lld |", c, t[1 + 3 * c], t[2 + 3 * c], t[3 + 3 * c], t[32 + 2 * c], t[33 + 2 * c]);
+      fprintf(stderr, " epi %lld staged %lld bar %lld end %lld\n", t[56], t[58], t[59], t[57]);
     }
   }
   return RGNN_OK;

@@ -248,6 +248,16 @@ extern "C" int rgnn_version(void) { return RGNN_VERSION; }
 extern "C" const char* rgnn_last_error(void) { return g_err; }
 extern "C" int64_t rgnn_launch_count(void) { return (int64_t)g_launches.load(); }
 
+extern "C" int rgnn_set_weight_cache(int enable) {
+  gemm_weight_cache_enable(enable != 0);
+  if (!enable) gemm_weight_cache_clear();
+  return RGNN_OK;
+}
+extern "C" int rgnn_weight_cache_clear(void) {
+  gemm_weight_cache_clear();
+  return RGNN_OK;
+}
+
 extern "C" size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, int32_t d_in, int32_t d_out,
                                        int32_t mlp_layers) {
   if (plan == nullptr || d_in <= 0 || d_out <= 0) return 0;

@@ -40,6 +40,8 @@ SIGNATURES = {
     "rgnn_plan_num_edge_types": (c_int32, [_PTR]),
     "rgnn_plan_num_edges": (c_int64, [_PTR]),
     "rgnn_plan_export": (c_int, [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "rgnn_set_weight_cache": (c_int, [c_int]),
+    "rgnn_weight_cache_clear": (c_int, []),
     "rgnn_workspace_bytes": (c_size_t, [_PTR, c_int, c_int32, c_int32, c_int32]),
     "rgnn_rgcn_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int, c_int, c_int,
                                   _PTR, _PTR, c_size_t, _PTR]),
@@ -110,6 +112,40 @@ def launch_count() -> int:
     return int(load_library().rgnn_launch_count())
 
 
+_weight_cache_on = False
+_weight_versions: Dict[int, int] = {}
+
+
+def set_weight_cache(enable: bool):
+    """Static-weight mode (inference / benchmarking): keep the GEMM's packed weight images across calls
+    (rgnn_set_weight_cache in include/rgnn.h).  In-place updates of weight tensors are detected through
+    ``Tensor._version`` the next time they are passed to a layer function and flush the cache."""
+    global _weight_cache_on
+    check(load_library().rgnn_set_weight_cache(1 if enable else 0))
+    _weight_cache_on = bool(enable)
+    _weight_versions.clear()
+
+
+def weight_cache_clear():
+    check(load_library().rgnn_weight_cache_clear())
+    _weight_versions.clear()
+
+
+def note_weights(tensors):
+    """Called by the layer functions with every weight tensor they are about to pass down."""
+    if not _weight_cache_on:
+        return
+    stale = False
+    for t in tensors:
+        key, ver = t.data_ptr(), t._version
+        old = _weight_versions.get(key)
+        if old is not None and old != ver:
+            stale = True
+        _weight_versions[key] = ver
+    if stale:
+        check(load_library().rgnn_weight_cache_clear())
+
+
 def current_stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -131,6 +167,7 @@ def as_f32(t: torch.Tensor, what: str) -> torch.Tensor:
 
 def ptr_table(tensors: Sequence[torch.Tensor]):
     """Host array of device pointers (the 'host array of L device pointers' of include/rgnn.h)."""
+    note_weights(tensors)
     arr = (c_void_p * max(len(tensors), 1))()
     for i, t in enumerate(tensors):
         arr[i] = t.data_ptr()

@@ -4,6 +4,7 @@ from typing import Dict, Optional
 import torch
 
 from ..utils import LAYER_GGNN, CELL_GRU, get_aggregation_function, get_gated_unit
+from ..engine import note_weights
 from ._common import (RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, load_library, prepare, ptr_table,
                       weight_list, workspace)
 
@@ -38,6 +39,7 @@ def sparse_ggnn_layer(node_embeddings: torch.Tensor,
         raise RgnnError(RGNN_E_INVALID, "sparse_ggnn_layer: cell weights must be [%d,%d], [%d,%d], [%d]; got %s %s %s"
                         % (d_out, gates * d_out, d_out, gates * d_out, gates * d_out,
                            tuple(kernel.shape), tuple(rec.shape), tuple(bias.shape)))
+    note_weights([kernel, rec, bias])
     lib = load_library()
     out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
     with torch.cuda.device(h.device):
