@@ -85,6 +85,13 @@ RGNN_API int64_t rgnn_launch_count(void);
  */
 RGNN_API int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t num_edge_types,
                      const int32_t* const* adjacency_lists, const int64_t* num_edges, void* stream);
+/* Same, with flags.  RGNN_PLAN_DEFERRED_CHECK: do not synchronise; the index-range check result stays on the
+ * device until rgnn_plan_status() (which synchronises the creation stream) is called.  Out-of-range ids are
+ * clamped to node 0 inside the plan, so later kernels stay memory-safe either way. */
+#define RGNN_PLAN_DEFERRED_CHECK 1
+RGNN_API int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t num_edge_types,
+                        const int32_t* const* adjacency_lists, const int64_t* num_edges, int flags, void* stream);
+RGNN_API int rgnn_plan_status(const rgnn_plan_t* plan);
 RGNN_API int rgnn_plan_destroy(rgnn_plan_t* plan);
 RGNN_API int32_t rgnn_plan_num_nodes(const rgnn_plan_t* plan);
 RGNN_API int32_t rgnn_plan_num_edge_types(const rgnn_plan_t* plan);
@@ -115,6 +122,15 @@ RGNN_API int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* node_embedd
                       int activation, int aggregation, int normalize_by_num_incoming,
                       int use_both_source_and_target, int num_timesteps,
                       float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* graph_num_layers x sparse_rgcn_layer in one call -- the GNN loop of
+ * Sparse_Graph_Model.__build_graph_propagation_model (models/sparse_graph_model.py:176-191) without the scaffold's
+ * dropout / residual / inter-layer Dense.  edge_weights: host array of num_layers * L pointers (layer-major),
+ * every kernel [d, d]; the layers share activation / aggregation / normalisation like RGCN_Model does. */
+RGNN_API int rgnn_rgcn_stack_forward(const rgnn_plan_t* plan, const float* node_embeddings, int32_t d, int32_t num_layers,
+                            const float* const* edge_weights, const float* num_incoming,
+                            int activation, int aggregation, int normalize_by_num_incoming,
+                            float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- gnns/ggnn.py:8-95  sparse_ggnn_layer --------------------------------------------------
  * cell_kernel [d, 3d] (GRU, gates z|r|h) or [d, d] (RNN); cell_recurrent_kernel same shape;

@@ -278,3 +278,26 @@ def test_weight_cache_tracks_in_place_updates(cuda_device):
                                                    activation_function="tanh", weights=w2), "cache flushed on update")
     finally:
         G.set_weight_cache(False)
+
+
+def test_rgcn_layer_stack_equals_layer_by_layer(cuda_device):
+    import torch
+    import tf_gnn_samples_b200 as G
+    b = batching.ppi_like_batch(num_nodes=700, num_links=9000, seed=8)
+    h = torch.as_tensor(node_states(b.num_nodes, 128)).to(cuda_device)
+    cnt = torch.as_tensor(b.type_to_num_incoming_edges).to(cuda_device)
+    ws = [W.to_torch(W.rgcn_weights(3, 128, 128, seed=20 + i), cuda_device) for i in range(3)]
+    plan = GraphPlan(b.adjacency_lists, b.num_nodes, device=cuda_device, validate=False)   # deferred index check
+    plan.check()
+    cur = h
+    for w in ws:
+        cur = sparse_rgcn_layer(cur, plan, cnt, 128, activation_function="ReLU", weights=w)
+    stacked = G.rgcn_layer_stack(h, plan, cnt, ws, activation_function="ReLU")
+    assert torch.equal(cur, stacked)
+
+
+def test_deferred_plan_check_reports_bad_ids(cuda_device):
+    bad = [np.array([[0, 1], [2, 99]], dtype=np.int32)]
+    plan = GraphPlan(bad, 10, device=cuda_device, validate=False)      # no exception yet: check is deferred
+    with pytest.raises(RgnnError):
+        plan.check()

@@ -65,11 +65,22 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 __device__ __forceinline__ float hard_sigmoid(float x) {                 // Keras hard_sigmoid (TF1 GRU default)
   return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f);
 }
+static __device__ __noinline__ float4 slow_act4(float4 v, int act) {     // one call per 4 elements
+  switch (act) {
+    case RGNN_ACT_TANH: return make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+    case RGNN_ACT_GELU:
+      return make_float4(v.x * (0.5f * (1.0f + erff(v.x * 0.70710678118654752f))), v.y * (0.5f * (1.0f + erff(v.y * 0.70710678118654752f))),
+                         v.z * (0.5f * (1.0f + erff(v.z * 0.70710678118654752f))), v.w * (0.5f * (1.0f + erff(v.w * 0.70710678118654752f))));
+    default: return make_float4(slow_act(v.x, act), slow_act(v.y, act), slow_act(v.z, act), slow_act(v.w, act));
+  }
+}
 __device__ __forceinline__ float4 act4(float4 v, int act) {
   if (act == RGNN_ACT_LINEAR) return v;
-  v.x = apply_act(v.x, act); v.y = apply_act(v.y, act);
-  v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
-  return v;
+  if (act == RGNN_ACT_RELU) return make_float4(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f), fmaxf(v.z, 0.0f), fmaxf(v.w, 0.0f));
+  if (act == RGNN_ACT_LEAKY_RELU)
+    return make_float4(v.x > 0.0f ? v.x : 0.2f * v.x, v.y > 0.0f ? v.y : 0.2f * v.y, v.z > 0.0f ? v.z : 0.2f * v.z,
+                       v.w > 0.0f ? v.w : 0.2f * v.w);
+  return slow_act4(v, act);
 }
 
 // read-only 128-bit load through the non-coherent path (tables written by a previous kernel)

@@ -329,6 +329,29 @@ extern "C" int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* h, int32_
   return RGNN_OK;
 }
 
+// models/sparse_graph_model.py:176-191: for layer_idx in range(graph_num_layers): _apply_gnn_layer(...)
+extern "C" int rgnn_rgcn_stack_forward(const rgnn_plan_t* plan, const float* h, int32_t d, int32_t num_layers,
+                                       const float* const* edge_weights, const float* num_incoming, int activation,
+                                       int aggregation, int normalize, float* out, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  RGNN_REQUIRE(plan != nullptr && num_layers >= 1, "rgcn_stack: plan is NULL or num_layers < 1");
+  RGNN_REQUIRE(edge_weights != nullptr, "rgcn_stack: edge_weights is NULL");
+  const size_t row_bytes = align_up((size_t)plan->V * d * sizeof(float), 256);
+  RGNN_REQUIRE(workspace != nullptr && workspace_bytes > 2 * row_bytes, "rgcn_stack: workspace too small");
+  char* base = static_cast<char*>(workspace);
+  float* buf[2] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + row_bytes)};
+  void* inner = base + 2 * row_bytes;
+  const size_t inner_bytes = workspace_bytes - 2 * row_bytes;
+  const float* cur = h;
+  for (int l = 0; l < num_layers; ++l) {
+    float* dst = (l == num_layers - 1) ? out : buf[l & 1];
+    RGNN_PROPAGATE(rgnn_rgcn_forward(plan, cur, d, d, edge_weights + (size_t)l * plan->L, num_incoming, activation,
+                                     aggregation, normalize, 0, 1, dst, inner, inner_bytes, stream_));
+    cur = dst;
+  }
+  return RGNN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // gnns/ggnn.py:8-95
 // ---------------------------------------------------------------------------------------------

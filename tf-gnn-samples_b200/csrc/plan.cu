@@ -84,7 +84,14 @@ using namespace rgnn;
 
 extern "C" int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t num_edge_types,
                                 const int32_t* const* adjacency_lists, const int64_t* num_edges, void* stream_) {
+  return rgnn_plan_create_ex(out, num_nodes, num_edge_types, adjacency_lists, num_edges, 0, stream_);
+}
+
+extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t num_edge_types,
+                                   const int32_t* const* adjacency_lists, const int64_t* num_edges, int flags,
+                                   void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool deferred = (flags & RGNN_PLAN_DEFERRED_CHECK) != 0;
   RGNN_REQUIRE(out != nullptr, "plan_create: out is NULL");
   *out = nullptr;
   RGNN_REQUIRE(num_nodes >= 0, "plan_create: num_nodes %d < 0", num_nodes);
@@ -141,7 +148,7 @@ extern "C" int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t nu
   const size_t off_bytes = align_up(sizeof(int32_t) * ((size_t)num_nodes + 1), 256);
   const size_t m_bytes = align_up(sizeof(int32_t) * Mz, 256);
   plan->stream = stream;
-  PLAN_CUDA(cudaMallocAsync(&plan->block, off_bytes + 5 * m_bytes, stream));
+  PLAN_CUDA(cudaMallocAsync(&plan->block, off_bytes + 5 * m_bytes + 256, stream));
   {
     char* b = static_cast<char*>(plan->block);
     plan->seg_off = reinterpret_cast<int32_t*>(b);
@@ -150,11 +157,13 @@ extern "C" int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t nu
     plan->e_orig = reinterpret_cast<int32_t*>(b + off_bytes + 2 * m_bytes);
     plan->o_src = reinterpret_cast<int32_t*>(b + off_bytes + 3 * m_bytes);
     plan->o_tgt = reinterpret_cast<int32_t*>(b + off_bytes + 4 * m_bytes);
+    plan->err_flag = reinterpret_cast<int*>(b + off_bytes + 5 * m_bytes);
   }
+  PLAN_CUDA(cudaMemsetAsync(plan->err_flag, 0, sizeof(int), stream));
 
   if (M == 0) {
     PLAN_CUDA(cudaMemsetAsync(plan->seg_off, 0, sizeof(int32_t) * ((size_t)num_nodes + 1), stream));
-    PLAN_CUDA(cudaStreamSynchronize(stream));
+    if (!deferred) PLAN_CUDA(cudaStreamSynchronize(stream));
     *out = plan;
     return RGNN_OK;
   }
@@ -168,15 +177,15 @@ extern "C" int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t nu
     PLAN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, (int)M, 0, end_bit, stream));
   }
   const size_t arr = align_up(sizeof(uint32_t) * Mz, 256);
-  const size_t total = 4 * arr + 256 + align_up(cub_bytes, 256);
+  const size_t total = 4 * arr + align_up(cub_bytes, 256);
   char* scratch = nullptr;
   PLAN_CUDA(cudaMallocAsync(&scratch, total, stream));
   uint32_t* k0 = reinterpret_cast<uint32_t*>(scratch);
   uint32_t* k1 = reinterpret_cast<uint32_t*>(scratch + arr);
   int32_t* v0 = reinterpret_cast<int32_t*>(scratch + 2 * arr);
   int32_t* v1 = reinterpret_cast<int32_t*>(scratch + 3 * arr);
-  int* err = reinterpret_cast<int*>(scratch + 4 * arr);
-  void* cub_tmp = scratch + 4 * arr + 256;
+  int* err = plan->err_flag;
+  void* cub_tmp = scratch + 4 * arr;
 
   auto fail_scratch = [&](int code) {
     cudaFreeAsync(scratch, stream);
@@ -192,7 +201,6 @@ extern "C" int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t nu
     }                                                                                                      \
   } while (0)
 
-  PLAN_CUDA2(cudaMemsetAsync(err, 0, sizeof(int), stream));
   {
     dim3 grid((maxE + 255) / 256, num_edge_types);
     plan_concat_kernel<<<grid, 256, 0, stream>>>(tab, num_nodes, num_edge_types, plan->o_src, plan->o_tgt, k0, v0, err);
@@ -209,18 +217,28 @@ extern "C" int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t nu
     PLAN_CUDA2(cudaGetLastError());
     count_launch();
   }
-  int herr = 0;
-  PLAN_CUDA2(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, stream));
   PLAN_CUDA2(cudaFreeAsync(scratch, stream));
-  PLAN_CUDA2(cudaStreamSynchronize(stream));
-  if (herr != 0) {
-    set_error("plan_create: adjacency list holds a node index outside [0, %d)", num_nodes);
-    return fail(RGNN_E_INVALID);
+  if (!deferred) {
+    const int rc = rgnn_plan_status(plan);
+    if (rc != RGNN_OK) return fail(rc);
   }
   *out = plan;
   return RGNN_OK;
 #undef PLAN_CUDA
 #undef PLAN_CUDA2
+}
+
+extern "C" int rgnn_plan_status(const rgnn_plan_t* plan) {
+  RGNN_REQUIRE(plan != nullptr, "plan_status: plan is NULL");
+  if (plan->err_flag == nullptr) return RGNN_OK;
+  int herr = 0;
+  RGNN_CHECK_CUDA(cudaMemcpyAsync(&herr, plan->err_flag, sizeof(int), cudaMemcpyDeviceToHost, plan->stream));
+  RGNN_CHECK_CUDA(cudaStreamSynchronize(plan->stream));
+  if (herr != 0) {
+    set_error("plan: adjacency list holds a node index outside [0, %d)", plan->V);
+    return RGNN_E_INVALID;
+  }
+  return RGNN_OK;
 }
 
 extern "C" int rgnn_plan_destroy(rgnn_plan_t* plan) {

@@ -17,6 +17,7 @@ struct rgnn_plan {
   int32_t type_off[RGNN_MAX_EDGE_TYPES + 1] = {0};   // host copy: block of type l = [type_off[l], type_off[l+1])
   int32_t max_type_edges = 0;
   int device = 0;
+  int* err_flag = nullptr;      // device flag: an adjacency list held an out-of-range node id
   void* block = nullptr;        // the one pool allocation behind all arrays above
   cudaStream_t stream = nullptr; // creation stream (the block is freed stream-ordered on it)
 };

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __
   if (v >= p.V) return;
   const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
   const int dh = p.D / p.K;   // per-head width, multiple of 4 (checked on the host)
+  const int col0 = blockIdx.y * (128 * NV) + lane * 4;   // heads are independent: a warp owns a column slice
 
   bool ok[NV];
   int head[NV];
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __
   float mx[NV], den[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const int col = k * 128 + lane * 4;
+    const int col = col0 + k * 128;
     ok[k] = col < p.D;
     head[k] = ok[k] ? col / dh : 0;
     acc[k] = f4(0.0f);
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __
         if (j + u < n) {
           const int src = __shfl_sync(0xffffffffu, my_src, j + u);
           const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
-          const float* row = p.table + ((size_t)src * p.L + ty) * p.D + lane * 4;
+          const float* row = p.table + ((size_t)src * p.L + ty) * p.D + col0;
           const float* ss = p.s_src + (size_t)src * LK + (size_t)ty * p.K;
           const float* st = p.s_tgt + (size_t)v * LK + (size_t)ty * p.K;
 #pragma unroll
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __
       }
     }
   }
-  float* orow = p.out + (size_t)v * p.D + lane * 4;
+  float* orow = p.out + (size_t)v * p.D + col0;
 #pragma unroll
   for (int k = 0; k < NV; ++k)
     if (ok[k]) {
@@ -397,19 +398,14 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
 
 int launch_seg_rgat(const RgatParams& p, cudaStream_t stream) {
   RGNN_REQUIRE(p.D > 0 && (p.D % 4) == 0 && p.K >= 1 && (p.D % p.K) == 0, "rgat: state dim %d / heads %d invalid", p.D, p.K);
-  if (p.D > RGNN_MAX_STATE_DIM || ((p.D / p.K) % 4) != 0) {
-    set_error("rgat: state dim %d (max %d) with per-head dim %d (must be a multiple of 4) not supported", p.D,
-              RGNN_MAX_STATE_DIM, p.D / p.K);
+  if (((p.D / p.K) % 4) != 0) {
+    set_error("rgat: per-head dim %d (state dim %d / %d heads) must be a multiple of 4 in this build", p.D / p.K, p.D, p.K);
     return RGNN_E_UNSUPPORTED;
   }
   if (p.V == 0) return RGNN_OK;
-  const dim3 grid((p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  switch (nv_for(p.D)) {
-    case 1: seg_rgat_kernel<1><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
-    case 2: seg_rgat_kernel<2><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
-    case 3: seg_rgat_kernel<3><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
-    default: seg_rgat_kernel<4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
-  }
+  // one warp per 128-column slice of a target row (heads are independent; more resident warps win here)
+  const dim3 grid((p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (p.D + 127) / 128);
+  seg_rgat_kernel<1><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return RGNN_OK;

@@ -35,6 +35,8 @@ SIGNATURES = {
     "rgnn_last_error": (c_char_p, []),
     "rgnn_launch_count": (c_int64, []),
     "rgnn_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int32, c_int32, _PTR, _PTR, _PTR]),
+    "rgnn_plan_create_ex": (c_int, [ctypes.POINTER(c_void_p), c_int32, c_int32, _PTR, _PTR, c_int, _PTR]),
+    "rgnn_plan_status": (c_int, [_PTR]),
     "rgnn_plan_destroy": (c_int, [_PTR]),
     "rgnn_plan_num_nodes": (c_int32, [_PTR]),
     "rgnn_plan_num_edge_types": (c_int32, [_PTR]),
@@ -58,10 +60,10 @@ SIGNATURES = {
     "rgnn_segment_aggregate": (c_int, [_PTR, _PTR, c_int32, c_int, _PTR, _PTR]),
     "rgnn_dense_forward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
     "rgnn_layer_norm": (c_int, [_PTR, c_int32, c_int32, _PTR, _PTR, _PTR, _PTR]),
-    "rgnn_rgcn_stack_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, c_int, _PTR, _PTR, c_int, c_int, c_int,
+    "rgnn_rgcn_stack_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int,
                                         _PTR, _PTR, c_size_t, _PTR]),
 }
-OPTIONAL_SYMBOLS = {"rgnn_rgcn_stack_forward"}
+OPTIONAL_SYMBOLS = set()
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -197,7 +199,10 @@ class GraphPlan:
     copied to ``device`` like a feed_dict would).
     """
 
-    def __init__(self, adjacency_lists: Sequence, num_nodes: int, device: Optional[torch.device] = None):
+    def __init__(self, adjacency_lists: Sequence, num_nodes: int, device: Optional[torch.device] = None,
+                 validate: bool = True):
+        """validate=True: synchronise and raise RgnnError if an adjacency list holds a node id outside [0, V)
+        (what TF does at sess.run).  validate=False: fully asynchronous build; ``check()`` reports later."""
         lib = load_library()
         adj: List[torch.Tensor] = []
         for a in adjacency_lists:
@@ -226,8 +231,8 @@ class GraphPlan:
         ptrs = ptr_table(dev_adj)
         handle = c_void_p()
         with torch.cuda.device(device):
-            check(lib.rgnn_plan_create(ctypes.byref(handle), self.num_nodes, self.num_edge_types, ptrs, counts,
-                                       current_stream_ptr(device)))
+            check(lib.rgnn_plan_create_ex(ctypes.byref(handle), self.num_nodes, self.num_edge_types, ptrs, counts,
+                                          0 if validate else 1, current_stream_ptr(device)))
         self._handle = handle
         self.num_edges = int(lib.rgnn_plan_num_edges(handle))
 
@@ -236,6 +241,10 @@ class GraphPlan:
         if self._handle is None:
             raise RgnnError(RGNN_E_INVALID, "GraphPlan used after close()")
         return self._handle
+
+    def check(self):
+        """Synchronise the creation stream and raise if the index-range check failed (deferred validation)."""
+        check(load_library().rgnn_plan_status(self.handle))
 
     def export(self) -> Dict[str, torch.Tensor]:
         """Copies of the plan arrays (tests / debugging)."""

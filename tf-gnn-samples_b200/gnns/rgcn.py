@@ -45,3 +45,31 @@ def sparse_rgcn_layer(node_embeddings: torch.Tensor,
                                     out.data_ptr(), ws_buf.data_ptr(), ws_buf.numel(),
                                     current_stream_ptr(h.device)))
     return out
+
+
+def rgcn_layer_stack(node_embeddings: torch.Tensor, adjacency_lists, type_to_num_incoming_edges,
+                     layer_weights: List[Dict[str, List[torch.Tensor]]],
+                     activation_function: Optional[str] = "ReLU", message_aggregation_function: str = "sum",
+                     normalize_by_num_incoming: bool = True, *, plan=None) -> torch.Tensor:
+    """graph_num_layers x sparse_rgcn_layer in ONE library call (rgnn_rgcn_stack_forward): the GNN loop of
+    Sparse_Graph_Model.__build_graph_propagation_model (models/sparse_graph_model.py:176-191) for RGCN_Model,
+    without the scaffold's dropout / residual / inter-layer Dense.  Same result as calling sparse_rgcn_layer
+    once per entry of ``layer_weights``; saves the per-layer host overhead."""
+    act = get_activation(activation_function)
+    agg = get_aggregation_function(message_aggregation_function)
+    h, plan, d_in, d_out = prepare(node_embeddings, adjacency_lists, plan, None)
+    L = plan.num_edge_types
+    flat = []
+    for w in layer_weights:
+        flat.extend(weight_list(w, "edge_weights", L, (d_in, d_in), "rgcn_layer_stack"))
+    cnt = num_incoming_tensor(type_to_num_incoming_edges, plan, normalize_by_num_incoming)
+    lib = load_library()
+    out = torch.empty((plan.num_nodes, d_in), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        nbytes = lib.rgnn_workspace_bytes(plan.handle, LAYER_RGCN, d_in, d_in, 0) + 2 * (plan.num_nodes * d_in * 4 + 256)
+        ws_buf = workspace(h.device, nbytes)
+        check(lib.rgnn_rgcn_stack_forward(plan.handle, h.data_ptr(), d_in, len(layer_weights), ptr_table(flat),
+                                          cnt.data_ptr() if cnt is not None else None, act, agg,
+                                          int(bool(normalize_by_num_incoming)), out.data_ptr(), ws_buf.data_ptr(),
+                                          ws_buf.numel(), current_stream_ptr(h.device)))
+    return out
