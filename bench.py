@@ -327,15 +327,18 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(nb for (_, nb, _, _) in offsets.values())
     d2h = out_host.numel() * 4
 
-    def dev_view(name):
+    def dev_view(buf, name):
         o, nb, dt, shape = offsets[name]
         tdt = torch.float32 if dt == np.float32 else torch.int32
-        return stage_dev[o:o + nb].view(tdt).view(*shape)
+        return buf[o:o + nb].view(tdt).view(*shape)
 
     def e2e_step():
-        stage_dev.copy_(stage_host, non_blocking=True)        # H2D of this step's inputs
-        hd, cd = dev_view("h"), dev_view("cnt")
-        ad = [dev_view("adj%d" % i) for i in range(L)]
+        stage_dev.copy_(stage_host, non_blocking=True)        # H2D of this step's inputs (one DMA)
+        # One device-side copy out of the DMA landing buffer: kernels reading the landing buffer directly ran
+        # 3-4x slower on this platform (tools/e2e_probe.py: plan 341 vs 82 us, layers 382 vs 135 us).
+        work = stage_dev.clone()
+        hd, cd = dev_view(work, "h"), dev_view(work, "cnt")
+        ad = [dev_view(work, "adj%d" % i) for i in range(L)]
         p = G.GraphPlan(ad, V, device=dev, validate=False)    # index check stays on the device ...
         cur = G.rgcn_layer_stack(hd, p, cd, ws, activation_function="ReLU")
         out_host.copy_(cur, non_blocking=True)                # D2H of the step's result

@@ -118,7 +118,7 @@ class NodeRangePartition:
             need = need[(need >= self.lo) & (need < self.hi)]
             self.send_local_idx.append(need - self.lo)
         self.send_counts = np.array([x.shape[0] for x in self.send_local_idx], dtype=np.int64)
-        self.halo_bytes_per_row = None
+        self._idx_cache = {}
 
     def exchange(self, h_own, group=None):
         """[n_own, D] owned states -> [n_local, D] = owned rows followed by the halo rows, via one
@@ -127,8 +127,12 @@ class NodeRangePartition:
         import torch.distributed as dist
         assert h_own.shape[0] == self.n_own
         D = h_own.shape[1]
-        idx = torch.as_tensor(np.concatenate(self.send_local_idx) if self.send_counts.sum() else np.zeros(0, np.int64),
-                              device=h_own.device)
+        key = str(h_own.device)
+        idx = self._idx_cache.get(key)
+        if idx is None:   # index list is fixed per batch: build it on the device once
+            idx = torch.as_tensor(np.concatenate(self.send_local_idx) if self.send_counts.sum() else np.zeros(0, np.int64),
+                                  device=h_own.device)
+            self._idx_cache[key] = idx
         send = h_own.index_select(0, idx) if idx.numel() else h_own.new_zeros((0, D))
         recv = h_own.new_empty((self.n_halo, D))
         if self.world_size > 1:
