@@ -307,8 +307,8 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- e2e: host buffers -> public API -> host ----------------
     if args.skip_e2e:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms_per_step, "layer_ms": layer_ms,
-                              "warm_l2_ms_per_step": warm_ms, "note": "profiling run (--skip-e2e): not a bench line"}))
+            emit({"metric": METRIC, "value": value, "ms_per_step": ms_per_step, "layer_ms": layer_ms,
+                  "warm_l2_ms_per_step": warm_ms, "note": "profiling run (--skip-e2e): not a bench line"})
         return
     # One pinned staging buffer holds the step's host inputs back to back (features | adjacency lists |
     # in-degrees), so the step does ONE host->device copy; every section starts 256-byte aligned.
@@ -398,7 +398,18 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1 and not args.skip_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(batch, h0, layer_weights)
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
 
 
 def main():
@@ -417,6 +428,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # The contract is ONE JSON line on stdout.  Native libraries print there too (NCCL's version banner at the
+    # first communicator), so fd 1 is pointed at stderr for the whole run and the JSON line is written to the
+    # saved real stdout at the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch
         import torch.distributed as dist
