@@ -33,9 +33,9 @@ constexpr int TC_GROUPS = 2;                 // producer groups alternate K chun
 constexpr int TC_GROUP_WARPS = 4;            // one group covers the 128-row tile: 4 warps x 32 rows of TMEM lanes
 constexpr int TC_PRODUCER_WARPS = TC_GROUPS * TC_GROUP_WARPS;
 constexpr int TC_GROUP_THREADS = 32 * TC_GROUP_WARPS;
-constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + 2);   // + MMA warp + B-loader warp
 constexpr int A_IMG_BYTES = TC_BM * 128;     // 16 KB
-constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
+constexpr size_t TC_SMEM_MAX = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t TC_RING_BUDGET = TC_SMEM_MAX - 1024 /*align*/ - 18432 /*epilogue staging*/ - 512 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -189,89 +189,85 @@ __global__ void __launch_bounds__(256) pack_b_kernel(const __grid_constant__ Pac
 }
 
 // -------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised kernel.  Roles (14 warps):
+//   warps 0-3   epilogue: TMEM -> registers -> padded smem staging -> coalesced global stores
+//   warps 4-11  A producers, two groups of 4 warps alternating K chunks
+//   warp 12     MMA issuer (one elected thread) + TMEM alloc / dealloc
+//   warp 13     B loader (one elected thread, TMA bulk copies of the packed weight images)
+// Each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is double-buffered in TMEM
+// (2 x BN_alloc columns), so the write-back of tile i overlaps the mainloop of tile i+1.
+// -------------------------------------------------------------------------------------------------
+constexpr int EPI_WARPS = 4;
+constexpr int PROD_WARP0 = EPI_WARPS;
+constexpr int MMA_WARP = PROD_WARP0 + TC_PRODUCER_WARPS;
+constexpr int BLOAD_WARP = MMA_WARP + 1;
+constexpr int TC_THREADS_V4 = 32 * (BLOAD_WARP + 1);
+constexpr int EPI_COLS = 32;                       // columns staged per epilogue step
+constexpr int EPI_PITCH = (EPI_COLS + 4) * 4;      // bytes; 144: 8 consecutive rows hit 8 distinct 16-byte bank groups
+constexpr int EPI_STAGE_BYTES = TC_BM * EPI_PITCH; // 18 KB
+
 struct TcParams {
   GemmParams g;
   const float* packed;     // pack_b output (per z for ROW_RANGES / COL_BLOCKS: z * packed_stride floats)
   size_t packed_stride;
   int BN, stages, chunks1, chunks2;
   int n_total;             // columns of C covered by this launch (batch*N for SHARED_A, else N)
-  int tmem_cols;
-  int ring_bytes;          // operand ring, at least as large as the epilogue's [128][BN+4] staging tile
-  long long* trace;        // RGNN_GEMM_TRACE=1: per-CTA clock64 timeline (debug only), else nullptr
+  int n_tiles;
+  int tmem_cols;           // total allocation (two accumulators of tmem_cols/2 columns)
+  int ring_bytes;
+  int total_tiles;
+  int tile_start[RGNN_MAX_EDGE_TYPES + 1];   // first tile of batch entry z (ROW_RANGES / COL_BLOCKS), else {0, total}
 };
 
-// trace slots (clock64 relative to kernel entry): 0 prologue done; 1+3c producer got stage; 2+3c loads landed;
-// 3+3c arrived (c < 8); 32+2c MMA saw full; 33+2c MMA committed (c < 8); 56 epilogue start; 57 epilogue end
-#define TC_TRACE(slot)                                                                          \
-  do {                                                                                          \
-    if (p.trace != nullptr) p.trace[(size_t)cta_lin * 64 + (slot)] = clock64() - t_entry;       \
-  } while (0)
+struct TileInfo { int z, m0, row_end, n_tile; };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t) {
+  TileInfo ti;
+  const GemmParams& g = p.g;
+  int z = 0;
+  if (g.batch_mode == BATCH_ROW_RANGES || g.batch_mode == BATCH_COL_BLOCKS) {
+    while (t >= p.tile_start[z + 1]) ++z;
+  }
+  const int local = t - p.tile_start[z];
+  const int row_begin = (g.batch_mode == BATCH_ROW_RANGES) ? g.row_off[z] : 0;
+  ti.z = z;
+  ti.row_end = (g.batch_mode == BATCH_ROW_RANGES) ? g.row_off[z + 1] : g.M;
+  ti.m0 = row_begin + (local / p.n_tiles) * TC_BM;
+  ti.n_tile = local % p.n_tiles;
+  return ti;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const long long t_entry = clock64();
-  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   const GemmParams& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN, S = p.stages;
   const int b_img_bytes = BN * 128;
   const int stage_bytes = 2 * A_IMG_BYTES + 2 * b_img_bytes;
-  // 1024-byte aligned operand ring (32-bit shared addresses), then barriers
-  const uint32_t smem_base = smem_u32(smem_raw);
-  const uint32_t ring = (smem_base + 1023u) & ~1023u;
-  const uint32_t full0 = ring + (uint32_t)p.ring_bytes, empty0 = full0 + 8 * S, accum_bar = full0 + 16 * S;
-  const uint32_t tmem_slot = accum_bar + 8;
-
-  // ---- operands of this CTA ----
-  const int z = blockIdx.z;
-  const float* A1 = g.A1;
-  float* C = g.C;
-  int row_begin = 0, row_end = g.M;
-  const float* packed = p.packed;
-  if (g.batch_mode == BATCH_ROW_RANGES) {
-    row_begin = g.row_off[z]; row_end = g.row_off[z + 1];
-    packed += (size_t)z * p.packed_stride;
-  } else if (g.batch_mode == BATCH_COL_BLOCKS) {
-    A1 += (size_t)z * g.K1;
-    C += (size_t)z * g.N;
-    packed += (size_t)z * p.packed_stride;
-  }
-  const int m0 = row_begin + blockIdx.y * TC_BM;
-  if (m0 >= row_end) return;                       // uniform across the CTA, before any barrier / allocation
-  const int n_tile = blockIdx.x, n0 = n_tile * BN;
   const int nchunks = p.chunks1 + p.chunks2;
+  // shared-memory map (32-bit shared addresses): operand ring | epilogue staging | barriers | tmem slot
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t estage = ring + (uint32_t)p.ring_bytes;
+  const uint32_t full0 = estage + EPI_STAGE_BYTES, empty0 = full0 + 8 * S;
+  const uint32_t tfull0 = empty0 + 8 * S, tempty0 = tfull0 + 16;
+  const uint32_t tmem_slot = tempty0 + 16;
+  const int acc_cols = p.tmem_cols / 2;
+  const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
-  // A-producer helper: the 8 float4 of chunk c this thread owns (rows ptid/8 + 16 i, 16-byte column ptid%8)
-  const int group = warp / TC_GROUP_WARPS;          // producer group (meaningful for warps < TC_PRODUCER_WARPS)
-  const int ptid = tid % TC_GROUP_THREADS;          // thread index inside the group
-  auto load_a_chunk = [&](int c, float4 (&v)[8]) {
-    const bool seg2 = c >= p.chunks1;
-    const int k0 = (seg2 ? c - p.chunks1 : c) * TC_BK;
-    const int Kseg = seg2 ? g.K2 : g.K1;
-    const float* Abase = seg2 ? g.A2 : A1;
-    const int lda = seg2 ? g.lda2 : g.lda1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int f = ptid + i * TC_GROUP_THREADS;
-      const int row = f >> 3, c16 = f & 7;
-      const int grow = m0 + row, gk = k0 + c16 * 4;
-      v[i] = (grow < row_end && gk < Kseg) ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)grow * lda + gk))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  float4 va[8];
-  if (warp < TC_PRODUCER_WARPS && group < nchunks) load_a_chunk(group, va);   // in flight while barriers / TMEM are set up
-
-  if (warp == TC_PRODUCER_WARPS && lane == 0) {
+  if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full0 + 8 * s, TC_GROUP_THREADS + 1);         // 128 producer arrivals + the B loader's expect_tx arrival
-      mbar_init(empty0 + 8 * s, 1);                           // one tcgen05.commit
+      mbar_init(full0 + 8 * s, TC_GROUP_THREADS + 1);   // one producer group + the B loader's expect_tx arrival
+      mbar_init(empty0 + 8 * s, 1);                     // one tcgen05.commit
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);                     // accumulator complete (tcgen05.commit)
+      mbar_init(tempty0 + 8 * a, EPI_WARPS);            // accumulator drained (one lane per epilogue warp)
+    }
     fence_barrier_init();
   }
   __syncwarp();
-  if (warp == TC_PRODUCER_WARPS) {                  // TMEM allocation by the MMA warp (it also frees it)
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -279,19 +275,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = lds32(tmem_slot);
-  if (tid == 0) TC_TRACE(0);
 
-  if (warp < TC_PRODUCER_WARPS) {
+  if (warp >= PROD_WARP0 && warp < MMA_WARP) {
     // =========================== A producers ===========================
-    // Two producer groups alternate chunks (group g owns chunks g, g+2, ...).  A thread issues the loads of
-    // its NEXT chunk right after publishing the current one, so they fly while the other group converts:
-    // fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the membar waits for the issuing
-    // thread's outstanding loads -- prefetching inside one group would be serialised by it (r01 trace).
-    for (int c = group; c < nchunks; c += TC_GROUPS) {
-      const int s = c % S;
-      const uint32_t use = c / S;
-      if (c >= S) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
-      if (ptid == 0 && c < 8) TC_TRACE(1 + 3 * c);
+    // Group g owns the chunks q = g, g+2, ... of this CTA's flat (tile, chunk) sequence.  A thread issues the
+    // loads of its NEXT chunk right after publishing the current one: fence.proxy.async lowers to
+    // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the membar waits for the issuing thread's outstanding loads, so the
+    // prefetch has to live in the other group's time slot, not inside this thread's store phase.
+    const int group = (warp - PROD_WARP0) / TC_GROUP_WARPS;
+    const int ptid = tid - 32 * PROD_WARP0 - group * TC_GROUP_THREADS;
+    const int total_q = my_tiles * nchunks;
+    auto load_a_chunk = [&](int q, float4 (&v)[8]) {
+      const int ti_idx = q / nchunks, c = q - ti_idx * nchunks;
+      const TileInfo ti = decode_tile(p, (int)blockIdx.x + ti_idx * (int)gridDim.x);
+      const bool seg2 = c >= p.chunks1;
+      const int k0 = (seg2 ? c - p.chunks1 : c) * TC_BK;
+      const int Kseg = seg2 ? g.K2 : g.K1;
+      const float* Abase = seg2 ? g.A2 : (g.batch_mode == BATCH_COL_BLOCKS ? g.A1 + (size_t)ti.z * g.K1 : g.A1);
+      const int lda = seg2 ? g.lda2 : g.lda1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int f = ptid + i * TC_GROUP_THREADS;
+        const int row = f >> 3, c16 = f & 7;
+        const int grow = ti.m0 + row, gk = k0 + c16 * 4;
+        v[i] = (grow < ti.row_end && gk < Kseg) ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)grow * lda + gk))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 va[8];
+    if (group < total_q) load_a_chunk(group, va);
+    for (int q = group; q < total_q; q += TC_GROUPS) {
+      const int s = q % S;
+      const int use = q / S;
+      if (use > 0) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
       const uint32_t a_hi = ring + (uint32_t)(s * stage_bytes);
       const uint32_t a_lo = a_hi + A_IMG_BYTES;
 #pragma unroll
@@ -307,119 +323,136 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
       }
       fence_proxy_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(full0 + 8 * s);
-      if (ptid == 0 && c < 8) TC_TRACE(3 + 3 * c);
-      if (c + TC_GROUPS < nchunks) load_a_chunk(c + TC_GROUPS, va);
+      if (q + TC_GROUPS < total_q) load_a_chunk(q + TC_GROUPS, va);
     }
-    // =========================== epilogue ===========================
-    // TMEM -> registers (thread = row) -> padded smem tile -> row-contiguous reads: bias / activation /
-    // GRU math and 128-bit stores are coalesced along the row (the thread-per-row stores of v1 cost 6000
-    // cycles per tile).  The operand ring is free: accum_bar fires after the last MMA has read it.
-    mbar_wait(accum_bar, 0);
-    if (tid == 0) TC_TRACE(56);
-    __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
-    tc_fence_after_sync();
-    const uint32_t stile = ring;                    // [128][BN + 4] fp32
-    const uint32_t lds = (uint32_t)(BN + 4) * 4;    // row pitch in bytes
-    {
-      const int quarter = warp % TC_GROUP_WARPS;    // a warp may only touch TMEM lanes [32*(warp%4), +32)
-      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      const uint32_t srow = stile + (uint32_t)(quarter * 32 + lane) * lds;
-      for (int cb = group * 16; cb < BN; cb += 16 * TC_GROUPS) {   // the two groups split the 16-column blocks
-        float v[16];
-        tmem_ld16(lane_base + cb, v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          sts128(srow + (uint32_t)(cb + q * 4) * 4, make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]));
-      }
-    }
-    if (tid == 0) TC_TRACE(58);
-    asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");   // producer warps only
-    if (tid == 0) TC_TRACE(59);
-    const int dgru = (g.epi == EPI_GRU_ZR) ? g.N / 2 : g.N;
-    constexpr int ROWS_PER_WARP = TC_BM / TC_PRODUCER_WARPS;
-    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-      const int r = m0 + warp * ROWS_PER_WARP + rr;
-      if (r >= row_end) break;
-      const uint32_t srow = stile + (uint32_t)(warp * ROWS_PER_WARP + rr) * lds;
-      for (int c4 = lane; c4 < BN / 4; c4 += 32) {
-        const int c = n0 + c4 * 4;
-        if (c >= p.n_total) break;
-        float4 o = lds128(srow + (uint32_t)c4 * 16);
-        if (g.bias != nullptr) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + c));
-          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-        }
-        if (g.epi == EPI_STORE) {
-          o = act4(o, g.act);
-          *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = o;
-        } else if (g.epi == EPI_GRU_ZR) {
-          o.x = hard_sigmoid(o.x); o.y = hard_sigmoid(o.y); o.z = hard_sigmoid(o.z); o.w = hard_sigmoid(o.w);
-          if (c < dgru) {
-            *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = o;                      // z gate
-          } else {
-            const int cc = c - dgru;
-            const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + cc));
-            *reinterpret_cast<float4*>(g.C2 + (size_t)r * g.ldc2 + cc) = make_float4(o.x * h.x, o.y * h.y, o.z * h.z, o.w * h.w);
-          }
-        } else {  // EPI_GRU_OUT: h' = z*h + (1-z)*act(.)
-          o = act4(o, g.act);
-          const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + c));
-          const float4 zz = __ldg(reinterpret_cast<const float4*>(g.aux_z + (size_t)r * g.ld_z + c));
-          *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) =
-              make_float4(zz.x * h.x + (1.0f - zz.x) * o.x, zz.y * h.y + (1.0f - zz.y) * o.y,
-                          zz.z * h.z + (1.0f - zz.z) * o.z, zz.w * h.w + (1.0f - zz.w) * o.w);
-        }
-      }
-    }
-    if (tid == 0) TC_TRACE(57);
-  } else if (warp == TC_PRODUCER_WARPS) {
+  } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (one thread) ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % S;
-        mbar_wait(full0 + 8 * s, (c / S) & 1);
-        if (c < 8) TC_TRACE(32 + 2 * c);
+      int q = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int a = it & 1;
+        if (it >= 2) mbar_wait(tempty0 + 8 * a, ((it >> 1) - 1) & 1);   // epilogue has drained this accumulator
         tc_fence_after_sync();
-        const uint32_t a_hi = ring + (uint32_t)(s * stage_bytes);
-        const uint32_t a_lo = a_hi + A_IMG_BYTES;
-        const uint32_t b_hi = a_lo + A_IMG_BYTES;
-        const uint32_t b_lo = b_hi + b_img_bytes;
-        const uint64_t da_hi = make_sw128_desc(a_hi), da_lo = make_sw128_desc(a_lo);
-        const uint64_t db_hi = make_sw128_desc(b_hi), db_lo = make_sw128_desc(b_lo);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * acc_cols);
+        for (int c = 0; c < nchunks; ++c, ++q) {
+          const int s = q % S;
+          mbar_wait(full0 + 8 * s, (q / S) & 1);
+          tc_fence_after_sync();
+          const uint32_t a_hi = ring + (uint32_t)(s * stage_bytes);
+          const uint32_t a_lo = a_hi + A_IMG_BYTES;
+          const uint32_t b_hi = a_lo + A_IMG_BYTES;
+          const uint32_t b_lo = b_hi + b_img_bytes;
+          const uint64_t da_hi = make_sw128_desc(a_hi), da_lo = make_sw128_desc(a_lo);
+          const uint64_t db_hi = make_sw128_desc(b_hi), db_lo = make_sw128_desc(b_lo);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {       // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (>>4 units)
-          const uint64_t adv = (uint64_t)(k * 2);
-          umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (c | k) != 0);   // small terms first
-          umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1);
-          umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1);
+          for (int k = 0; k < TC_BK / 8; ++k) {     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (>>4 units)
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, (c | k) != 0);   // small terms first
+            umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1);
+          }
+          umma_commit(empty0 + 8 * s);              // stage reusable once these MMAs have read it
         }
-        umma_commit(empty0 + 8 * s);                // stage reusable once these MMAs have read it
-        if (c < 8) TC_TRACE(33 + 2 * c);
+        umma_commit(tfull0 + 8 * a);                // accumulator complete -> epilogue
       }
-      umma_commit(accum_bar);                       // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else if (warp == BLOAD_WARP) {
+    // =========================== B loader (TMA bulk copies of the packed images) ===========================
+    if (lane == 0) {
+      int q = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const TileInfo ti = decode_tile(p, (int)blockIdx.x + it * (int)gridDim.x);
+        const float* src_tile = p.packed + (size_t)ti.z * p.packed_stride + (size_t)ti.n_tile * nchunks * 2 * (BN * TC_BK);
+        for (int c = 0; c < nchunks; ++c, ++q) {
+          const int s = q % S;
+          const int use = q / S;
+          if (use > 0) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
+          const uint32_t b_hi = ring + (uint32_t)(s * stage_bytes + 2 * A_IMG_BYTES);
+          mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);
+          bulk_copy_g2s(b_hi, src_tile + (size_t)c * 2 * (BN * TC_BK), 2 * b_img_bytes, full0 + 8 * s);   // hi and lo are adjacent
+        }
+      }
     }
     __syncwarp();
   } else {
-    // =========================== B loader (TMA bulk copies of the packed images) ===========================
-    if (lane == 0) {
-      const float* src_tile = packed + (size_t)n_tile * nchunks * 2 * (BN * TC_BK);
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % S;
-        if (c >= S) mbar_wait(empty0 + 8 * s, ((c / S) - 1) & 1);
-        const uint32_t b_hi = ring + (uint32_t)(s * stage_bytes + 2 * A_IMG_BYTES);
-        if (c < 8) TC_TRACE(2 + 3 * c);
-        mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);
-        bulk_copy_g2s(b_hi, src_tile + (size_t)c * 2 * (BN * TC_BK), 2 * b_img_bytes, full0 + 8 * s);   // hi and lo are adjacent
+    // =========================== epilogue warps ===========================
+    // Per 32-column block: tcgen05.ld (thread = row) -> padded smem -> 8 lanes per row read 128 contiguous bytes,
+    // so every global store instruction writes 4 full 128-byte lines; all 8 stores of a block are in flight.
+    const int quarter = warp;                        // warps 0-3 own TMEM lanes [32*warp, 32*warp+32)
+    const uint32_t srow_w = estage + (uint32_t)(quarter * 32 + lane) * EPI_PITCH;
+    const int sub_row = lane >> 3, sub_c4 = lane & 7;  // read mapping: 4 rows x 8 float4 per instruction
+    const int dgru = (EPI == EPI_GRU_ZR) ? g.N / 2 : g.N;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int a = it & 1;
+      const TileInfo ti = decode_tile(p, (int)blockIdx.x + it * (int)gridDim.x);
+      float* C = g.C + (g.batch_mode == BATCH_COL_BLOCKS ? (size_t)ti.z * g.N : 0);
+      const int n0 = ti.n_tile * BN;
+      mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
+      __syncwarp();
+      tc_fence_after_sync();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_cols);
+      for (int cb = 0; cb < BN; cb += EPI_COLS) {
+        {
+          float v[16];
+          tmem_ld16(lane_base + cb, v);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            sts128(srow_w + (uint32_t)(qd * 16), make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]));
+          tmem_ld16(lane_base + cb + 16, v);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            sts128(srow_w + (uint32_t)(64 + qd * 16), make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]));
+        }
+        __syncwarp();
+        const int c = n0 + cb + sub_c4 * 4;
+        const bool col_ok = c < p.n_total;
+        float4 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = lds128(estage + (uint32_t)(quarter * 32 + j * 4 + sub_row) * EPI_PITCH + (uint32_t)sub_c4 * 16);
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = ti.m0 + quarter * 32 + j * 4 + sub_row;
+          if (r < ti.row_end && col_ok) {
+            float4 x = make_float4(o[j].x + bias4.x, o[j].y + bias4.y, o[j].z + bias4.z, o[j].w + bias4.w);
+            if (EPI == EPI_STORE) {
+              x = act4(x, g.act);
+              *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = x;
+            } else if (EPI == EPI_GRU_ZR) {
+              x.x = hard_sigmoid(x.x); x.y = hard_sigmoid(x.y); x.z = hard_sigmoid(x.z); x.w = hard_sigmoid(x.w);
+              if (c < dgru) {
+                *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = x;                      // z gate
+              } else {
+                const int cc = c - dgru;
+                const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + cc));
+                *reinterpret_cast<float4*>(g.C2 + (size_t)r * g.ldc2 + cc) = make_float4(x.x * h.x, x.y * h.y, x.z * h.z, x.w * h.w);
+              }
+            } else {  // EPI_GRU_OUT: h' = z*h + (1-z)*act(.)
+              x = act4(x, g.act);
+              const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + c));
+              const float4 zz = __ldg(reinterpret_cast<const float4*>(g.aux_z + (size_t)r * g.ld_z + c));
+              *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) =
+                  make_float4(zz.x * h.x + (1.0f - zz.x) * x.x, zz.y * h.y + (1.0f - zz.y) * x.y,
+                              zz.z * h.z + (1.0f - zz.z) * x.z, zz.w * h.w + (1.0f - zz.w) * x.w);
+            }
+          }
+        }
+        __syncwarp();                               // staging rows are rewritten by the next column block
       }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * a);  // this warp's TMEM lanes of accumulator a are drained
     }
-    __syncwarp();
   }
 
   // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == TC_PRODUCER_WARPS) {
+  if (warp == MMA_WARP) {
     tc_fence_after_sync();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
   }
@@ -428,7 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tcgen05_kernel(const __gri
 int pick_bn(long m_tiles, int n_total, int gz) {
   int best = 32;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 32; bn -= 16) {
+  for (int bn = 256; bn >= 32; bn -= 32) {   // the epilogue stages 32-column blocks
     const long ctas = m_tiles * ((n_total + bn - 1) / bn) * gz;
     const long waves = (ctas + 147) / 148;
     const double cost = (double)waves * (96.0 + bn);   // per-tile time ~ fixed overhead + columns
@@ -495,6 +528,7 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   RGNN_REQUIRE(g.bias == nullptr || aligned16(g.bias), "gemm: bias must be 16-byte aligned");
   const int rows = (g.batch_mode == BATCH_ROW_RANGES) ? g.max_rows : g.M;
   if (rows <= 0) return RGNN_OK;
+
   TcParams p;
   p.g = g;
   p.chunks1 = (g.K1 + TC_BK - 1) / TC_BK;
@@ -504,12 +538,31 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   const int gz = (g.batch_mode == BATCH_ROW_RANGES || g.batch_mode == BATCH_COL_BLOCKS) ? g.batch : 1;
   p.BN = pick_bn((rows + TC_BM - 1) / TC_BM, p.n_total, gz);
   const int n_tiles = (p.n_total + p.BN - 1) / p.BN;
+  p.n_tiles = n_tiles;
+  // tile table: batch entry z owns tiles [tile_start[z], tile_start[z+1])
+  p.tile_start[0] = 0;
+  if (g.batch_mode == BATCH_ROW_RANGES) {
+    for (int z = 0; z < g.batch; ++z) {
+      const int rz = g.row_off[z + 1] - g.row_off[z];
+      p.tile_start[z + 1] = p.tile_start[z] + ((rz + TC_BM - 1) / TC_BM) * n_tiles;
+    }
+    p.total_tiles = p.tile_start[g.batch];
+  } else if (g.batch_mode == BATCH_COL_BLOCKS) {
+    for (int z = 0; z < g.batch; ++z) p.tile_start[z + 1] = p.tile_start[z] + ((g.M + TC_BM - 1) / TC_BM) * n_tiles;
+    p.total_tiles = p.tile_start[g.batch];
+  } else {
+    p.total_tiles = ((g.M + TC_BM - 1) / TC_BM) * n_tiles;
+    p.tile_start[1] = p.total_tiles;
+  }
+  if (p.total_tiles <= 0) return RGNN_OK;
+
   const size_t stage_bytes = 2 * (size_t)A_IMG_BYTES + 2 * (size_t)p.BN * 128;
-  p.stages = (int)(TC_SMEM_BUDGET / stage_bytes);
+  p.stages = (int)(TC_RING_BUDGET / stage_bytes);
   if (p.stages > 4) p.stages = 4;
-  if (p.stages > nchunks) p.stages = nchunks;
   if (p.stages < 1) p.stages = 1;
-  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  p.ring_bytes = (int)(p.stages * stage_bytes);
+  const int acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  p.tmem_cols = 2 * acc_cols;                                   // double-buffered accumulator
   p.packed_stride = (size_t)n_tiles * nchunks * 2 * p.BN * TC_BK;
   const size_t need = align_up(p.packed_stride * sizeof(float) * gz, 1024);
   bool need_pack = true;
@@ -558,39 +611,29 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
     count_launch();
   }
 
-  const size_t epi_tile = (size_t)TC_BM * (p.BN + 4) * sizeof(float);
-  p.ring_bytes = (int)align_up(std::max((size_t)p.stages * stage_bytes, epi_tile), 1024);
-  const size_t smem = 1024 + (size_t)p.ring_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    attr_smem = 220 * 1024;
+  const size_t smem = 1024 + (size_t)p.ring_bytes + EPI_STAGE_BYTES + (2 * p.stages + 4) * sizeof(uint64_t) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+    RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI_GRU_ZR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+    RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI_GRU_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+    attr_set = true;
   }
-  dim3 grid(n_tiles, (rows + TC_BM - 1) / TC_BM, gz);
-  static const bool trace_on = getenv("RGNN_GEMM_TRACE") != nullptr;
-  const size_t n_ctas = (size_t)grid.x * grid.y * grid.z;
-  p.trace = nullptr;
-  if (trace_on) {   // debug only: synchronous, prints one timeline summary per launch to stderr
-    RGNN_CHECK_CUDA(cudaMalloc(&p.trace, n_ctas * 64 * sizeof(long long)));
-    RGNN_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, n_ctas * 64 * sizeof(long long), stream));
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int device = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (num_sms <= 0) num_sms = 148;
   }
-  gemm_tcgen05_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+  const dim3 grid(p.total_tiles < num_sms ? p.total_tiles : num_sms);   // persistent: at most one CTA per SM
+  switch (g.epi) {
+    case EPI_GRU_ZR: gemm_tcgen05_kernel<EPI_GRU_ZR><<<grid, TC_THREADS_V4, smem, stream>>>(p); break;
+    case EPI_GRU_OUT: gemm_tcgen05_kernel<EPI_GRU_OUT><<<grid, TC_THREADS_V4, smem, stream>>>(p); break;
+    default: gemm_tcgen05_kernel<EPI_STORE><<<grid, TC_THREADS_V4, smem, stream>>>(p); break;
+  }
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
-  if (trace_on) {
-    std::vector<long long> h(n_ctas * 64);
-    RGNN_CHECK_CUDA(cudaStreamSynchronize(stream));
-    RGNN_CHECK_CUDA(cudaMemcpy(h.data(), p.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    cudaFree(p.trace);
-    fprintf(stderr, "[gemm trace] M=%d N=%d K=%d+%d BN=%d stages=%d ctas=%zu chunks=%d\n", g.M, p.n_total, g.K1, g.K2, p.BN, p.stages, n_ctas, nchunks);
-    const size_t picks[3] = {0, n_ctas / 2, n_ctas - 1};
-    for (size_t pi = 0; pi < 3; ++pi) {
-      const long long* t = h.data() + picks[pi] * 64;
-      fprintf(stderr, "  cta %zu: prologue %lld |", picks[pi], t[0]);
-      for (int c = 0; c < 8 && c < nchunks; ++c) fprintf(stderr, " c%d got %lld Bissue %lld arrived %lld mma_full %lld mma_commit %lld |", c, t[1 + 3 * c], t[2 + 3 * c], t[3 + 3 * c], t[32 + 2 * c], t[33 + 2 * c]);
-      fprintf(stderr, " epi %lld staged %lld bar %lld end %lld\n", t[56], t[58], t[59], t[57]);
-    }
-  }
   return RGNN_OK;
 }
 
