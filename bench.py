@@ -385,10 +385,11 @@ def run_ours(args, rank, world, local_rank):
                    "weights": "static: packed TF32 hi/lo weight images cached across steps (rgnn_set_weight_cache)",
                    "warm_l2_ms_per_step": warm_ms, "per_layer_edges_per_s": M / (layer_ms * 1e-3)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "one RGCN layer = gemm_tf32x3 (node transform) + seg_reduce (edge stage)",
+                     "traffic": traffic, "kernel": "one RGCN layer = gemm_tcgen05_kernel (node transform, tcgen05 3xTF32) + seg_reduce_kernel (fused edge stage)",
                      "algorithmic_bytes_per_launch": layer_bytes, "ms_per_launch": layer_ms, "peak_source": peak_src,
-                     "note": "working set is L2-resident (compulsory traffic ~6 MB/layer): frac compares algorithmic bytes "
-                             "with HBM bandwidth, see DESIGN.md"},
+                     "note": "working set is L2-resident: DRAM traffic (ncu) is 11.8 MB per layer vs 130 MB algorithmic, so frac "
+                             "compares algorithmic bytes with the HBM copy peak; the binding resource is L2->SM delivery "
+                             "(165 MB per layer at ~7 TB/s), see DESIGN.md 5.3 and profiles/r01_final_kernels.txt"},
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3,
                 "what": "pinned host features+adjacency+in-degrees -> one H2D -> GraphPlan build -> rgcn_layer_stack (3 layers) "
