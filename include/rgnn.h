@@ -64,7 +64,7 @@ enum rgnn_aggregation { RGNN_AGG_SUM = 0, RGNN_AGG_MAX = 1, RGNN_AGG_MEAN = 2, R
 enum rgnn_cell { RGNN_CELL_RNN = 0, RGNN_CELL_GRU = 1 };
 enum rgnn_layer_kind {
   RGNN_LAYER_RGCN = 0, RGNN_LAYER_GGNN = 1, RGNN_LAYER_RGAT = 2, RGNN_LAYER_FILM = 3,
-  RGNN_LAYER_EDGE_MLP = 4, RGNN_LAYER_RGIN = 5
+  RGNN_LAYER_EDGE_MLP = 4, RGNN_LAYER_RGIN = 5, RGNN_LAYER_RGCN_BACKWARD = 6
 };
 
 typedef struct rgnn_plan rgnn_plan_t;
@@ -122,6 +122,20 @@ RGNN_API int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* node_embedd
                       int activation, int aggregation, int normalize_by_num_incoming,
                       int use_both_source_and_target, int num_timesteps,
                       float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of ONE timestep of sparse_rgcn_layer with source-only messages (use_both_source_and_target = 0):
+ * the gradients TensorFlow autodiff produces for gnns/rgcn.py:84-114 (models/sparse_graph_model.py:253-260).
+ *   out       forward output [V, d_out] (act' is evaluated from it; gelu recomputes the pre-activation)
+ *   grad_out  dLoss/d out [V, d_out]
+ *   grad_node_embeddings [V, d_in] or NULL; grad_edge_weights: host array of L device pointers [d_in, d_out] or NULL
+ * 'max' aggregation is not differentiated in this build (RGNN_E_UNSUPPORTED).  The first backward on a plan builds
+ * a reverse (by-source) index inside it (not thread-safe).  Workspace: rgnn_workspace_bytes(RGNN_LAYER_RGCN_BACKWARD). */
+RGNN_API int rgnn_rgcn_backward(const rgnn_plan_t* plan, const float* node_embeddings, int32_t d_in, int32_t d_out,
+                       const float* const* edge_weights, const float* num_incoming,
+                       int activation, int aggregation, int normalize_by_num_incoming,
+                       const float* out, const float* grad_out,
+                       float* grad_node_embeddings, float* const* grad_edge_weights,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* graph_num_layers x sparse_rgcn_layer in one call -- the GNN loop of
  * Sparse_Graph_Model.__build_graph_propagation_model (models/sparse_graph_model.py:176-191) without the scaffold's

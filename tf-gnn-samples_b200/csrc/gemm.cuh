@@ -15,6 +15,7 @@ enum GemmBatchMode {
   BATCH_SHARED_A = 1,   // z = type: A shared, B = bptr[z], C columns offset z * N            (T = H . [W_0|..|W_{L-1}])
   BATCH_ROW_RANGES = 2, // z = type: rows [row_off[z], row_off[z+1]) of A and C, B = bptr[z]   (per-edge MLP layers)
   BATCH_COL_BLOCKS = 3, // z = type: A columns offset z * K, B = bptr[z], C columns offset z * N (per-node MLP chains)
+  BATCH_K_BLOCKS_T = 4, // one GEMM with K = batch * k_block: B[(z, j), n] = bptr[z][n * ldb1 + j]  (d_H = d_T . [W_0|..|W_{L-1}]^T)
 };
 
 struct GemmParams {
@@ -39,6 +40,7 @@ struct GemmParams {
   const float* bptr2[RGNN_MAX_EDGE_TYPES];    // per-batch B2 (optional)
   int row_off[RGNN_MAX_EDGE_TYPES + 1];       // BATCH_ROW_RANGES
   int max_rows = 0;                           // max rows of any batch entry (grid sizing)
+  int k_block = 0;                            // BATCH_K_BLOCKS_T: rows of K contributed by each bptr[z] (its column count)
 };
 
 // Enqueue; returns RGNN_OK / error code.  All dims % 4 == 0, pointers 16-byte aligned.

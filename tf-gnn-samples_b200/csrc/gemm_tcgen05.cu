@@ -152,6 +152,7 @@ struct PackParams {
   int n_total;                            // total columns = blocks * block_cols
   int BN;
   int chunks1, chunks2;                   // ceil(K1/32), ceil(K2/32)
+  int transposed, k_block;                // transposed: B[(z, j), n] = b1[z][n * ldb1 + j], K = blocks * k_block
   float* out;                             // [n_tiles][chunks1+chunks2][2][BN*32]
 };
 
@@ -173,12 +174,23 @@ __global__ void __launch_bounds__(256) pack_b_kernel(const __grid_constant__ Pac
   float hi[4], lo[4];
   float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   if (n < p.n_total) {
-    const int blk = n / p.block_cols, col = n - blk * p.block_cols;
-    const float* src = (seg2 ? p.b2[blk] : p.b1[blk]) + col;
+    if (p.transposed) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = k0 + c16 * 4 + j;
-      if (k < Kseg) x[j] = __ldg(src + (size_t)k * ld);
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + c16 * 4 + j;
+        if (k < Kseg) {
+          const int blk = k / p.k_block, jj = k - blk * p.k_block;
+          x[j] = __ldg(p.b1[blk] + (size_t)n * ld + jj);
+        }
+      }
+    } else {
+      const int blk = n / p.block_cols, col = n - blk * p.block_cols;
+      const float* src = (seg2 ? p.b2[blk] : p.b1[blk]) + col;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + c16 * 4 + j;
+        if (k < Kseg) x[j] = __ldg(src + (size_t)k * ld);
+      }
     }
   }
 #pragma unroll
@@ -528,6 +540,8 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   RGNN_REQUIRE(g.bias == nullptr || aligned16(g.bias), "gemm: bias must be 16-byte aligned");
   const int rows = (g.batch_mode == BATCH_ROW_RANGES) ? g.max_rows : g.M;
   if (rows <= 0) return RGNN_OK;
+  RGNN_REQUIRE(g.batch_mode != BATCH_K_BLOCKS_T || (g.k_block > 0 && g.K1 == g.batch * g.k_block && g.K2 == 0),
+               "gemm: BATCH_K_BLOCKS_T needs K1 == batch * k_block and no second segment");
 
   TcParams p;
   p.g = g;
@@ -594,7 +608,11 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
     q.ldb1 = g.ldb1; q.ldb2 = g.ldb2; q.K1 = g.K1; q.K2 = g.K2;
     q.BN = p.BN; q.chunks1 = p.chunks1; q.chunks2 = p.chunks2;
     q.n_total = p.n_total;
-    if (g.batch_mode == BATCH_SHARED_A) {
+    q.transposed = 0; q.k_block = 0;
+    if (g.batch_mode == BATCH_K_BLOCKS_T) {
+      q.transposed = 1; q.k_block = g.k_block; q.block_cols = g.N;
+      for (int j = 0; j < g.batch; ++j) { q.b1[j] = g.bptr[j]; q.b2[j] = nullptr; }
+    } else if (g.batch_mode == BATCH_SHARED_A) {
       q.block_cols = g.N;
       for (int j = 0; j < g.batch; ++j) { q.b1[j] = g.bptr[j]; q.b2[j] = g.bptr2[j]; }
     } else if (g.batch_mode == BATCH_NONE) {
@@ -602,7 +620,7 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
     } else {
       q.block_cols = g.N; q.b1[0] = g.bptr[zz]; q.b2[0] = g.bptr2[zz];
     }
-    for (int j = 0; j < (g.batch_mode == BATCH_SHARED_A ? g.batch : 1); ++j) {
+    for (int j = 0; j < ((g.batch_mode == BATCH_SHARED_A || g.batch_mode == BATCH_K_BLOCKS_T) ? g.batch : 1); ++j) {
       RGNN_REQUIRE(q.b1[j] != nullptr && (g.K2 == 0 || q.b2[j] != nullptr), "gemm: weight pointer %d is NULL", j);
     }
     q.out = static_cast<float*>(pack_ws) + (size_t)zz * p.packed_stride;

@@ -221,6 +221,10 @@ int launch_bm(const GemmParams& p, int rows, cudaStream_t stream) {
 
 int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   RGNN_REQUIRE(p.M >= 0 && p.N > 0 && p.K1 > 0 && p.K2 >= 0, "gemm: bad dims M=%d N=%d K1=%d K2=%d", p.M, p.N, p.K1, p.K2);
+  if (p.batch_mode == BATCH_K_BLOCKS_T) {
+    set_error("gemm: the legacy mma.sync kernel has no transposed-weight mode (unset RGNN_GEMM_IMPL=mma)");
+    return RGNN_E_UNSUPPORTED;
+  }
   RGNN_REQUIRE((p.N % 4) == 0 && (p.K1 % 4) == 0 && (p.K2 % 4) == 0, "gemm: N, K must be multiples of 4 (N=%d K1=%d K2=%d)", p.N, p.K1, p.K2);
   RGNN_REQUIRE((p.lda1 % 4) == 0 && (p.ldb1 % 4) == 0 && (p.ldc % 2) == 0, "gemm: leading dims must keep 16-byte rows");
   RGNN_REQUIRE(p.batch >= 1 && p.batch <= RGNN_MAX_EDGE_TYPES, "gemm: batch %d out of range", p.batch);

@@ -118,7 +118,7 @@ int gemm_shared_a(Arena& ar, const float* A, int V, int K, const float* const* B
 }
 
 void seg_from_plan(SegParams& s, const rgnn_plan_t* plan) {
-  s.V = plan->V; s.L = plan->L;
+  s.V = plan->V; s.L = plan->L; s.scale_ld = plan->V;
   s.seg_off = plan->seg_off; s.e_type = plan->e_type; s.e_idx = plan->e_src;
 }
 
@@ -270,6 +270,7 @@ extern "C" size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, 
     case RGNN_LAYER_GGNN: floats = V * L * dm + 6 * V * dm; break;
     case RGNN_LAYER_RGAT: floats = V * L * dm + 2 * V * L * dm / 4 + 2 * V * dm; break;
     case RGNN_LAYER_FILM: floats = 3 * V * L * dm + 2 * V * dm; break;
+    case RGNN_LAYER_RGCN_BACKWARD: floats = 2 * V * L * dm + 2 * V * dm + 64 * L * dm * dm + 64 * 1024; break;
     case RGNN_LAYER_EDGE_MLP:
     case RGNN_LAYER_RGIN: {
       const size_t nl = (size_t)(mlp_layers > 0 ? mlp_layers : 1);
@@ -325,6 +326,82 @@ extern "C" int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* h, int32_
     s.out = dst; s.ld_out = d_out;
     RGNN_PROPAGATE(launch_seg_reduce(s, stream));
     cur = dst; din = d_out;
+  }
+  return RGNN_OK;
+}
+
+// Backward of ONE timestep of sparse_rgcn_layer (source-only messages): what tf.gradients produces for
+// gnns/rgcn.py:84-114 (the reference trains through TF autodiff, models/sparse_graph_model.py:253-260).
+//   d_agg = grad_out * act'(.) / div            (elementwise)
+//   d_T[u, l, :] = sum_{(u->v) in A_l} s_{l,v} * d_agg[v, :]      (sorted-segment kernel over the reverse index)
+//   d_H = d_T . [W_0|...|W_{L-1}]^T             (tcgen05 GEMM, transposed weight images)
+//   d_W_l = H^T . d_T[:, l, :]                  (tiled FMA kernel, deterministic two-stage sum)
+extern "C" int rgnn_rgcn_backward(const rgnn_plan_t* plan_c, const float* h, int32_t d_in, int32_t d_out,
+                                  const float* const* edge_weights, const float* num_incoming, int activation,
+                                  int aggregation, int normalize, const float* out, const float* grad_out,
+                                  float* grad_h, float* const* grad_edge_weights, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  rgnn_plan* plan = const_cast<rgnn_plan*>(plan_c);   // the reverse index is built lazily inside the plan
+  RGNN_REQUIRE(plan != nullptr && h != nullptr && out != nullptr && grad_out != nullptr && edge_weights != nullptr,
+               "rgcn_backward: NULL argument");
+  RGNN_REQUIRE(d_in > 0 && d_out > 0 && (d_in % 4) == 0 && (d_out % 4) == 0, "rgcn_backward: dims must be positive multiples of 4");
+  RGNN_PROPAGATE(check_act(activation, "rgcn_backward"));
+  RGNN_PROPAGATE(check_agg(aggregation, "rgcn_backward"));
+  if (aggregation == RGNN_AGG_MAX) {
+    set_error("rgcn_backward: the gradient of 'max' aggregation is not implemented in this build");
+    return RGNN_E_UNSUPPORTED;
+  }
+  RGNN_REQUIRE(!normalize || num_incoming != nullptr, "rgcn_backward: normalize_by_num_incoming needs type_to_num_incoming_edges");
+  RGNN_REQUIRE(gemm_use_tcgen05(), "rgcn_backward needs the tcgen05 GEMM (unset RGNN_GEMM_IMPL=mma)");
+  const int V = plan->V, L = plan->L;
+  RGNN_PROPAGATE(plan_ensure_reverse(plan, stream));
+  Arena ar(workspace, workspace_bytes);
+  float* d_agg = ar.floats((size_t)V * d_out);
+  float* d_t = ar.floats((size_t)V * L * d_out);
+  float* pre = nullptr;
+  float* t_fwd = nullptr;
+  if (activation == RGNN_ACT_GELU) {   // gelu' needs the pre-activation: recompute it (T = H.W, agg = segment reduce)
+    pre = ar.floats((size_t)V * d_out);
+    t_fwd = ar.floats((size_t)V * L * d_out);
+  }
+  float* gw_scratch = grad_edge_weights ? ar.floats(grad_weight_scratch_floats(V, L, d_in, d_out)) : nullptr;
+  RGNN_PROPAGATE(check_ws(ar, "rgcn_backward"));
+
+  if (pre != nullptr) {
+    RGNN_PROPAGATE(gemm_shared_a(ar, h, V, d_in, edge_weights, L, d_out, d_out, t_fwd, RGNN_ACT_LINEAR, stream));
+    SegParams f;
+    seg_from_plan(f, plan);
+    f.D = d_out; f.table = t_fwd; f.stride_idx = (long)L * d_out; f.stride_type = d_out;
+    f.num_incoming = normalize ? num_incoming : nullptr;
+    f.agg = aggregation; f.out = pre; f.ld_out = d_out;
+    RGNN_PROPAGATE(launch_seg_reduce(f, stream));
+  }
+  RGNN_PROPAGATE(launch_act_backward(grad_out, out, pre, V, d_out, activation, aggregation, plan->seg_off, d_agg, stream));
+  {
+    SegParams r;   // reverse index: segment = (source u, type l); gathered row = d_agg[original target]
+    r.V = V * L; r.L = L; r.D = d_out;
+    r.seg_off = plan->rev_seg_off; r.e_idx = plan->rev_src; r.e_type = plan->rev_type;
+    r.table = d_agg; r.stride_idx = d_out; r.stride_type = 0;
+    r.num_incoming = normalize ? num_incoming : nullptr; r.scale_ld = V; r.scale_by_idx = 1;
+    r.agg = RGNN_AGG_SUM; r.out = d_t; r.ld_out = d_out;
+    RGNN_PROPAGATE(launch_seg_reduce(r, stream));
+  }
+  if (grad_h != nullptr) {
+    GemmParams g;
+    g.A1 = d_t; g.lda1 = L * d_out; g.K1 = L * d_out;
+    g.M = V; g.N = d_in; g.C = grad_h; g.ldc = d_in; g.ldb1 = d_out;
+    g.batch_mode = BATCH_K_BLOCKS_T; g.batch = L; g.k_block = d_out;
+    for (int l = 0; l < L; ++l) { g.bptr[l] = edge_weights[l]; g.bptr2[l] = nullptr; }
+    RGNN_PROPAGATE(run_gemm(g, ar, stream));
+  }
+  if (grad_edge_weights != nullptr) {
+    GradWTable tab;
+    for (int l = 0; l < L; ++l) {
+      RGNN_REQUIRE(grad_edge_weights[l] != nullptr && aligned16(grad_edge_weights[l]), "rgcn_backward: grad weight %d is NULL / misaligned", l);
+      tab.out[l] = grad_edge_weights[l];
+    }
+    RGNN_PROPAGATE(launch_grad_weights(h, d_t, V, L, d_in, d_out, tab, gw_scratch, stream));
   }
   return RGNN_OK;
 }

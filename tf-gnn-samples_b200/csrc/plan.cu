@@ -60,6 +60,33 @@ __global__ void plan_finalize_kernel(const uint32_t* __restrict__ keys, const in
     for (int v = tgt + 1; v <= V; ++v) seg_off[v] = M;
 }
 
+struct TypeOffsets { int32_t off[RGNN_MAX_EDGE_TYPES + 1]; };
+
+// keys for the reverse index: (source * L + type) of every edge in original (type-major) order
+__global__ void plan_rev_keys_kernel(const __grid_constant__ TypeOffsets t, int L, const int32_t* __restrict__ o_src,
+                                     uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int l = blockIdx.y;
+  const int i = t.off[l] + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.off[l + 1]) return;
+  keys[i] = (uint32_t)o_src[i] * (uint32_t)L + (uint32_t)l;
+  vals[i] = i;
+}
+
+__global__ void plan_rev_finalize_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals,
+                                         const int32_t* __restrict__ o_tgt, int segments, int L, int M,
+                                         int32_t* __restrict__ seg_off, int32_t* __restrict__ r_src,
+                                         int32_t* __restrict__ r_type) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M) return;
+  const int seg = (int)keys[e];
+  r_src[e] = o_tgt[vals[e]];
+  r_type[e] = seg % L;
+  const int prev = (e == 0) ? -1 : (int)keys[e - 1];
+  for (int v = prev + 1; v <= seg; ++v) seg_off[v] = e;
+  if (e == M - 1)
+    for (int v = seg + 1; v <= segments; ++v) seg_off[v] = M;
+}
+
 void ensure_pool_config(int device) {
   static bool done[64] = {false};
   if (device < 0 || device >= 64 || done[device]) return;
@@ -78,6 +105,56 @@ int bits_for(uint64_t n) {   // number of low bits needed to represent values < 
 }
 
 }  // namespace
+
+int plan_ensure_reverse(rgnn_plan* plan, cudaStream_t stream) {
+  if (plan->rev_seg_off != nullptr) return RGNN_OK;
+  const int V = plan->V, L = plan->L;
+  const int M = (int)plan->M;
+  const size_t segments = (size_t)V * L;
+  const size_t off_bytes = align_up(sizeof(int32_t) * (segments + 1), 256);
+  const size_t m_bytes = align_up(sizeof(int32_t) * (size_t)(M > 0 ? M : 1), 256);
+  RGNN_CHECK_CUDA(cudaMallocAsync(&plan->rev_block, off_bytes + 2 * m_bytes, stream));
+  char* b = static_cast<char*>(plan->rev_block);
+  plan->rev_src = reinterpret_cast<int32_t*>(b + off_bytes);
+  plan->rev_type = reinterpret_cast<int32_t*>(b + off_bytes + m_bytes);
+  int32_t* seg_off = reinterpret_cast<int32_t*>(b);
+  if (M == 0) {
+    RGNN_CHECK_CUDA(cudaMemsetAsync(seg_off, 0, sizeof(int32_t) * (segments + 1), stream));
+    plan->rev_seg_off = seg_off;
+    return RGNN_OK;
+  }
+  const int end_bit = bits_for((uint64_t)segments);
+  size_t cub_bytes = 0;
+  {
+    cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr);
+    cub::DoubleBuffer<int32_t> dv(nullptr, nullptr);
+    RGNN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, M, 0, end_bit, stream));
+  }
+  const size_t arr = align_up(sizeof(uint32_t) * (size_t)M, 256);
+  char* scratch = nullptr;
+  RGNN_CHECK_CUDA(cudaMallocAsync(&scratch, 4 * arr + align_up(cub_bytes, 256), stream));
+  uint32_t* k0 = reinterpret_cast<uint32_t*>(scratch);
+  uint32_t* k1 = reinterpret_cast<uint32_t*>(scratch + arr);
+  int32_t* v0 = reinterpret_cast<int32_t*>(scratch + 2 * arr);
+  int32_t* v1 = reinterpret_cast<int32_t*>(scratch + 3 * arr);
+  TypeOffsets to;
+  for (int l = 0; l <= L; ++l) to.off[l] = plan->type_off[l];
+  plan_rev_keys_kernel<<<dim3((plan->max_type_edges + 255) / 256, L), 256, 0, stream>>>(to, L, plan->o_src, k0, v0);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  cub::DoubleBuffer<uint32_t> dk(k0, k1);
+  cub::DoubleBuffer<int32_t> dv(v0, v1);
+  RGNN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(scratch + 4 * arr, cub_bytes, dk, dv, M, 0, end_bit, stream));
+  plan_rev_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(dk.Current(), dv.Current(), plan->o_tgt,
+                                                                           (int)segments, L, M, seg_off, plan->rev_src,
+                                                                           plan->rev_type);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  RGNN_CHECK_CUDA(cudaFreeAsync(scratch, stream));
+  plan->rev_seg_off = seg_off;
+  return RGNN_OK;
+}
+
 }  // namespace rgnn
 
 using namespace rgnn;
@@ -243,6 +320,7 @@ extern "C" int rgnn_plan_status(const rgnn_plan_t* plan) {
 
 extern "C" int rgnn_plan_destroy(rgnn_plan_t* plan) {
   if (plan == nullptr) return RGNN_OK;
+  if (plan->rev_block != nullptr) cudaFreeAsync(plan->rev_block, plan->stream);
   if (plan->block != nullptr) cudaFreeAsync(plan->block, plan->stream);   // stream-ordered: safe after queued forwards
   delete plan;
   return RGNN_OK;

@@ -17,7 +17,18 @@ struct rgnn_plan {
   int32_t type_off[RGNN_MAX_EDGE_TYPES + 1] = {0};   // host copy: block of type l = [type_off[l], type_off[l+1])
   int32_t max_type_edges = 0;
   int device = 0;
+  // reverse index for the backward pass (built lazily by plan_ensure_reverse): CSR over (source, type) pairs,
+  // segment id = src * L + type; rev_src[e] = the edge's ORIGINAL target, rev_type[e] = its type
+  int32_t* rev_seg_off = nullptr;   // [V*L + 1]
+  int32_t* rev_src = nullptr;       // [M]
+  int32_t* rev_type = nullptr;      // [M]
+  void* rev_block = nullptr;
   int* err_flag = nullptr;      // device flag: an adjacency list held an out-of-range node id
   void* block = nullptr;        // the one pool allocation behind all arrays above
   cudaStream_t stream = nullptr; // creation stream (the block is freed stream-ordered on it)
 };
+
+namespace rgnn {
+// Build plan->rev_* on `stream` if absent (not thread-safe; called by the first backward on this plan).
+int plan_ensure_reverse(rgnn_plan* plan, cudaStream_t stream);
+}  // namespace rgnn

@@ -18,7 +18,9 @@ struct SegParams {
   const int32_t* e_type = nullptr;
   const float* table = nullptr;        // message row of edge e = table + e_idx[e]*stride_idx + e_type[e]*stride_type
   long stride_idx = 0, stride_type = 0;
-  const float* num_incoming = nullptr; // [L, V] fp32 -> s = 1/(c + 1e-7) (rgcn.py:100-104); NULL -> s = 1
+  const float* num_incoming = nullptr; // [L, scale_ld] fp32 -> s = 1/(c + 1e-7) (rgcn.py:100-104); NULL -> s = 1
+  int scale_ld = 0;                    // row length of num_incoming (number of graph nodes)
+  int scale_by_idx = 0;                // 0: c[type, v] of the segment's target v; 1: c[type, e_idx] (backward: the edge's original target)
   int msg_mode = MSG_LINEAR;
   const float* mod_table = nullptr;    // FILM: gamma at +0, beta at +D ; ADDTGT: q.  row = mod_table + v*mod_stride_node + type*mod_stride_type
   long mod_stride_node = 0, mod_stride_type = 0;
@@ -68,5 +70,17 @@ int launch_edge_build(const EdgeBuildParams& p, cudaStream_t stream);
 
 int launch_layer_norm(const float* x, int rows, int D, const float* gamma, const float* beta, float* out,
                       cudaStream_t stream);
+
+// d_agg[v, :] = grad_out[v, :] * act'(.) / div(v)   -- the elementwise head of every layer backward.
+// act' is evaluated from the forward OUTPUT for linear/tanh/relu/leaky_relu/elu/selu and from the
+// pre-activation `pre` (must be non-NULL) for gelu.  div: 1 (sum/max), n (mean), sqrt(n) (sqrt_n), n = max(in-degree, 1).
+int launch_act_backward(const float* grad_out, const float* out, const float* pre, int V, int D, int act, int agg,
+                        const int32_t* seg_off, float* d_agg, cudaStream_t stream);
+
+// grad_w[l][i][j] = sum_v h[v, i] * d_t[v, l, j]   (d_t is [V, L, D], h is [V, Din]); deterministic two-stage sum.
+struct GradWTable { float* out[RGNN_MAX_EDGE_TYPES]; };
+size_t grad_weight_scratch_floats(int V, int L, int d_in, int d_out);
+int launch_grad_weights(const float* h, const float* d_t, int V, int L, int d_in, int d_out, const GradWTable& out,
+                        float* scratch, cudaStream_t stream);
 
 }  // namespace rgnn

@@ -99,9 +99,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const 
     long my_off = 0;
     if (lane < n) {
       my_type = __ldg(p.e_type + e0 + lane);
-      my_off = (long)__ldg(p.e_idx + e0 + lane) * p.stride_idx + (long)my_type * p.stride_type;
+      const int idx = __ldg(p.e_idx + e0 + lane);
+      my_off = (long)idx * p.stride_idx + (long)my_type * p.stride_type;
       if (SCALED)   // 1.0f / (c + SMALL_NUMBER) evaluated in fp32 like the reference (rgcn.py:104)
-        my_scale = 1.0f / (__ldg(p.num_incoming + (size_t)my_type * p.V + v) + 1e-7f);
+        my_scale = 1.0f / (__ldg(p.num_incoming + (size_t)my_type * p.scale_ld + (p.scale_by_idx ? idx : v)) + 1e-7f);
     }
     for (int j = 0; j < n; j += UNROLL) {
       float4 r[UNROLL][NV];
@@ -327,6 +328,116 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) layer_norm_kernel(const 
     if (ok[k]) *reinterpret_cast<float4*>(out + (size_t)r * D + k * 128 + lane * 4) = v[k];
 }
 
+// ---- backward helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_grad_from_out(float o, int act) {
+  switch (act) {
+    case RGNN_ACT_TANH: return 1.0f - o * o;
+    case RGNN_ACT_RELU: return o > 0.0f ? 1.0f : 0.0f;
+    case RGNN_ACT_LEAKY_RELU: return o > 0.0f ? 1.0f : 0.2f;
+    case RGNN_ACT_ELU: return o > 0.0f ? 1.0f : o + 1.0f;                                   // d/dx (e^x - 1) = e^x = o + 1
+    case RGNN_ACT_SELU: return o > 0.0f ? 1.0507009873554805f : o + 1.0507009873554805f * 1.6732632423543772f;
+    default: return 1.0f;
+  }
+}
+__device__ __forceinline__ float gelu_grad(float x) {   // d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+
+__global__ void act_backward_kernel(const float* __restrict__ grad_out, const float* __restrict__ out,
+                                    const float* __restrict__ pre, int V, int D4, int act, int agg,
+                                    const int32_t* __restrict__ seg_off, float* __restrict__ d_agg) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)V * D4) return;
+  const int v = (int)(i / D4);
+  float inv = 1.0f;
+  if (agg == RGNN_AGG_MEAN || agg == RGNN_AGG_SQRT_N) {
+    const float n = fmaxf((float)(__ldg(seg_off + v + 1) - __ldg(seg_off + v)), 1.0f);
+    inv = 1.0f / (agg == RGNN_AGG_MEAN ? n : sqrtf(n));
+  }
+  const float4 g = ldg4(grad_out + i * 4);
+  float4 d;
+  if (act == RGNN_ACT_GELU) {
+    const float4 x = ldg4(pre + i * 4);
+    d = make_float4(gelu_grad(x.x), gelu_grad(x.y), gelu_grad(x.z), gelu_grad(x.w));
+  } else {
+    const float4 o = ldg4(out + i * 4);
+    d = make_float4(act_grad_from_out(o.x, act), act_grad_from_out(o.y, act), act_grad_from_out(o.z, act), act_grad_from_out(o.w, act));
+  }
+  *reinterpret_cast<float4*>(d_agg + i * 4) = make_float4(g.x * d.x * inv, g.y * d.y * inv, g.z * d.z * inv, g.w * d.w * inv);
+}
+
+// grad_w partials: CTA = 64 x 64 tile of one type's [Din, D] gradient over one slice of the node range.
+constexpr int GW_TILE = 64, GW_ROWS = 32;
+__global__ void __launch_bounds__(256) grad_weight_partial_kernel(const float* __restrict__ h, const float* __restrict__ d_t,
+                                                                 int V, int L, int d_in, int d_out, int splits,
+                                                                 float* __restrict__ partial) {
+  __shared__ float hs[GW_ROWS][GW_TILE + 4];
+  __shared__ float ts[GW_ROWS][GW_TILE + 4];
+  const int l = blockIdx.z / splits, sp = blockIdx.z % splits;
+  const int i0 = blockIdx.y * GW_TILE, j0 = blockIdx.x * GW_TILE;
+  const int rows_per = (V + splits - 1) / splits;
+  const int v0 = sp * rows_per, v1 = min(V, v0 + rows_per);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int vb = v0; vb < v1; vb += GW_ROWS) {
+    for (int f = threadIdx.x; f < GW_ROWS * (GW_TILE / 4); f += 256) {
+      const int r = f / (GW_TILE / 4), c4 = (f % (GW_TILE / 4)) * 4;
+      const int v = vb + r;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (v < v1) {
+        if (i0 + c4 < d_in) a = ldg4(h + (size_t)v * d_in + i0 + c4);
+        if (j0 + c4 < d_out) b = ldg4(d_t + ((size_t)v * L + l) * d_out + j0 + c4);
+      }
+      *reinterpret_cast<float4*>(&hs[r][c4]) = a;
+      *reinterpret_cast<float4*>(&ts[r][c4]) = b;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < GW_ROWS; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(&hs[r][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&ts[r][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+  float* dst = partial + ((size_t)(sp * L + l) * d_in) * d_out;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int i = i0 + ty * 4 + x;
+    if (i < d_in && j0 + tx * 4 < d_out)
+      *reinterpret_cast<float4*>(dst + (size_t)i * d_out + j0 + tx * 4) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+  }
+}
+
+__global__ void grad_weight_reduce_kernel(const float* __restrict__ partial, int L, int d_in, int d_out, int splits,
+                                          const __grid_constant__ GradWTable out) {
+  const long per_type = (long)d_in * d_out / 4;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_type * L) return;
+  const int l = (int)(i / per_type);
+  const long e = (i % per_type) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sp = 0; sp < splits; ++sp) {   // fixed order: deterministic
+    const float4 x = ldg4(partial + ((size_t)(sp * L + l) * d_in) * d_out + e);
+    s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+  }
+  *reinterpret_cast<float4*>(out.out[l] + e) = s;
+}
+
+inline int grad_weight_splits(int V, int L, int d_in, int d_out) {
+  const int tiles = ((d_in + GW_TILE - 1) / GW_TILE) * ((d_out + GW_TILE - 1) / GW_TILE) * L;
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  const int max_by_rows = (V + 63) / 64;
+  if (splits > max_by_rows) splits = max_by_rows;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
 inline int nv_for(int D) { return (D + 127) / 128; }
 
 }  // namespace
@@ -426,6 +537,37 @@ int launch_edge_build(const EdgeBuildParams& p, cudaStream_t stream) {
   if (p.max_type_edges == 0) return RGNN_OK;
   const dim3 grid((p.max_type_edges + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, p.L);
   edge_build_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+int launch_act_backward(const float* grad_out, const float* out, const float* pre, int V, int D, int act, int agg,
+                        const int32_t* seg_off, float* d_agg, cudaStream_t stream) {
+  RGNN_REQUIRE(D > 0 && (D % 4) == 0, "act backward: dim %d must be a positive multiple of 4", D);
+  RGNN_REQUIRE(act != RGNN_ACT_GELU || pre != nullptr, "act backward: gelu needs the pre-activation");
+  const long n = (long)V * (D / 4);
+  if (n == 0) return RGNN_OK;
+  act_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_out, out, pre, V, D / 4, act, agg, seg_off, d_agg);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+size_t grad_weight_scratch_floats(int V, int L, int d_in, int d_out) {
+  return (size_t)grad_weight_splits(V, L, d_in, d_out) * L * d_in * d_out;
+}
+
+int launch_grad_weights(const float* h, const float* d_t, int V, int L, int d_in, int d_out, const GradWTable& out,
+                        float* scratch, cudaStream_t stream) {
+  RGNN_REQUIRE((d_in % 4) == 0 && (d_out % 4) == 0, "grad weights: dims must be multiples of 4");
+  const int splits = grad_weight_splits(V, L, d_in, d_out);
+  const dim3 grid((d_out + GW_TILE - 1) / GW_TILE, (d_in + GW_TILE - 1) / GW_TILE, L * splits);
+  grad_weight_partial_kernel<<<grid, 256, 0, stream>>>(h, d_t, V, L, d_in, d_out, splits, scratch);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  const long n = (long)L * d_in * d_out / 4;
+  grad_weight_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(scratch, L, d_in, d_out, splits, out);
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return RGNN_OK;

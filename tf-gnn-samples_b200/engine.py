@@ -47,6 +47,8 @@ SIGNATURES = {
     "rgnn_workspace_bytes": (c_size_t, [_PTR, c_int, c_int32, c_int32, c_int32]),
     "rgnn_rgcn_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int, c_int, c_int,
                                   _PTR, _PTR, c_size_t, _PTR]),
+    "rgnn_rgcn_backward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR, _PTR,
+                                   _PTR, c_size_t, _PTR]),
     "rgnn_ggnn_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, _PTR, _PTR, c_int, c_int, c_int, c_int,
                                   _PTR, _PTR, c_size_t, _PTR]),
     "rgnn_rgat_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int,
