@@ -138,4 +138,4 @@ class RGCNPPIModel(torch.nn.Module):
                 if n > clip:
                     q.grad.mul_(clip / n)
         optimizer.step()
-        return {k: float(v) for k, v in m.items()}
+        return {k: float(v.detach()) for k, v in m.items()}
