@@ -71,3 +71,17 @@ def test_rgcn_grad_limits(cuda_device):
         sparse_rgcn_layer(h, adj, indeg, 64, message_aggregation_function="max", weights=w)
     with torch.no_grad():   # inference with max aggregation still works
         sparse_rgcn_layer(h, adj, indeg, 64, message_aggregation_function="max", weights=w)
+
+
+def test_rgcn_grads_with_heavy_segments(cuda_device):
+    """Zipf-skewed targets: heavy targets in the forward, heavy (source, type) pairs in the reverse index."""
+    b = batching.ppi_like_batch(num_nodes=800, num_links=40000, zipf_targets=True, seed=33)
+    D = 64
+    h = node_states(b.num_nodes, D, seed=34)
+    w = W.rgcn_weights(3, D, D, seed=35)
+    g = np.random.default_rng(36).standard_normal((b.num_nodes, D)).astype(np.float32)
+    out, d_h, d_ws = engine_grads(cuda_device, h, b.adjacency_lists, b.type_to_num_incoming_edges, w, g, "tanh", "sum", True, D)
+    want_h, want_ws = RG.rgcn_layer_grads(h, b.adjacency_lists, b.type_to_num_incoming_edges, g, "tanh", "sum", True, weights=w)
+    assert_parity(d_h, want_h, "d_h heavy")
+    for l in range(3):
+        assert_parity(d_ws[l], want_ws[l], "d_W[%d] heavy" % l)

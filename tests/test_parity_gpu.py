@@ -301,3 +301,29 @@ def test_deferred_plan_check_reports_bad_ids(cuda_device):
     plan = GraphPlan(bad, 10, device=cuda_device, validate=False)      # no exception yet: check is deferred
     with pytest.raises(RgnnError):
         plan.check()
+
+
+# ---------------- degree skew: heavy targets are reduced by a whole CTA (seg_reduce_heavy_kernel) ----------------
+@pytest.mark.parametrize("validate", [True, False])
+def test_heavy_segments_rgcn_and_film(cuda_device, validate):
+    import torch
+    b = batching.ppi_like_batch(num_nodes=1200, num_links=60000, zipf_targets=True, seed=21)
+    deg = b.type_to_num_incoming_edges.sum(axis=0)
+    assert deg.max() > 2000                                        # far beyond the 512-edge split threshold
+    plan = GraphPlan(b.adjacency_lists, b.num_nodes, device=cuda_device, validate=validate)
+    D = 128
+    h = node_states(b.num_nodes, D)
+    ht = torch.as_tensor(h).to(cuda_device)
+    cnt = torch.as_tensor(b.type_to_num_incoming_edges).to(cuda_device)
+    for agg in ("sum", "max", "mean"):
+        w = W.rgcn_weights(3, D, D, seed=31)
+        got = sparse_rgcn_layer(ht, plan, cnt, D, activation_function="tanh", message_aggregation_function=agg,
+                                weights=W.to_torch(w, cuda_device)).cpu().numpy()
+        want = R.sparse_rgcn_layer(h, b.adjacency_lists, b.type_to_num_incoming_edges, D, activation_function="tanh",
+                                   message_aggregation_function=agg, weights=w)
+        assert_parity(got, want, "heavy rgcn %s validate=%s" % (agg, validate))
+    w = W.film_weights(3, D, D, random_ln=True)
+    got = sparse_gnn_film_layer(ht, plan, cnt, D, normalize_by_num_incoming=True, weights=W.to_torch(w, cuda_device)).cpu().numpy()
+    want = R.sparse_gnn_film_layer(h, b.adjacency_lists, b.type_to_num_incoming_edges, D, normalize_by_num_incoming=True, weights=w)
+    assert_parity(got, want, "heavy film validate=%s" % validate)
+    plan.check()

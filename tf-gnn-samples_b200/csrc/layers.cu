@@ -119,6 +119,8 @@ int gemm_shared_a(Arena& ar, const float* A, int V, int K, const float* const* B
 
 void seg_from_plan(SegParams& s, const rgnn_plan_t* plan) {
   s.V = plan->V; s.L = plan->L; s.scale_ld = plan->V;
+  s.heavy_list = plan->heavy_list; s.heavy_count = plan->err_flag + 1;
+  s.heavy_threshold = RGNN_HEAVY_SEGMENT; s.heavy_known = plan->num_heavy_host;
   s.seg_off = plan->seg_off; s.e_type = plan->e_type; s.e_idx = plan->e_src;
 }
 
@@ -384,6 +386,8 @@ extern "C" int rgnn_rgcn_backward(const rgnn_plan_t* plan_c, const float* h, int
     r.seg_off = plan->rev_seg_off; r.e_idx = plan->rev_src; r.e_type = plan->rev_type;
     r.table = d_agg; r.stride_idx = d_out; r.stride_type = 0;
     r.num_incoming = normalize ? num_incoming : nullptr; r.scale_ld = V; r.scale_by_idx = 1;
+    r.heavy_list = plan->rev_heavy_list; r.heavy_count = plan->err_flag + 2;
+    r.heavy_threshold = RGNN_HEAVY_SEGMENT; r.heavy_known = -1;
     r.agg = RGNN_AGG_SUM; r.out = d_t; r.ld_out = d_out;
     RGNN_PROPAGATE(launch_seg_reduce(r, stream));
   }

@@ -87,6 +87,14 @@ __global__ void plan_rev_finalize_kernel(const uint32_t* __restrict__ keys, cons
     for (int v = seg + 1; v <= segments; ++v) seg_off[v] = M;
 }
 
+// append every segment longer than `threshold` to `list` (order is irrelevant: each is reduced independently)
+__global__ void plan_heavy_kernel(const int32_t* __restrict__ seg_off, int nseg, int threshold, int32_t* __restrict__ list,
+                                  int* __restrict__ count) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nseg) return;
+  if (seg_off[v + 1] - seg_off[v] > threshold) list[atomicAdd(count, 1)] = v;
+}
+
 void ensure_pool_config(int device) {
   static bool done[64] = {false};
   if (device < 0 || device >= 64 || done[device]) return;
@@ -113,8 +121,10 @@ int plan_ensure_reverse(rgnn_plan* plan, cudaStream_t stream) {
   const size_t segments = (size_t)V * L;
   const size_t off_bytes = align_up(sizeof(int32_t) * (segments + 1), 256);
   const size_t m_bytes = align_up(sizeof(int32_t) * (size_t)(M > 0 ? M : 1), 256);
-  RGNN_CHECK_CUDA(cudaMallocAsync(&plan->rev_block, off_bytes + 2 * m_bytes, stream));
+  RGNN_CHECK_CUDA(cudaMallocAsync(&plan->rev_block, off_bytes + 2 * m_bytes + off_bytes, stream));
   char* b = static_cast<char*>(plan->rev_block);
+  plan->rev_heavy_list = reinterpret_cast<int32_t*>(b + off_bytes + 2 * m_bytes);
+  RGNN_CHECK_CUDA(cudaMemsetAsync(plan->err_flag + 2, 0, sizeof(int), stream));
   plan->rev_src = reinterpret_cast<int32_t*>(b + off_bytes);
   plan->rev_type = reinterpret_cast<int32_t*>(b + off_bytes + m_bytes);
   int32_t* seg_off = reinterpret_cast<int32_t*>(b);
@@ -148,6 +158,10 @@ int plan_ensure_reverse(rgnn_plan* plan, cudaStream_t stream) {
   plan_rev_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(dk.Current(), dv.Current(), plan->o_tgt,
                                                                            (int)segments, L, M, seg_off, plan->rev_src,
                                                                            plan->rev_type);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  plan_heavy_kernel<<<(unsigned)((segments + 255) / 256), 256, 0, stream>>>(seg_off, (int)segments, RGNN_HEAVY_SEGMENT,
+                                                                         plan->rev_heavy_list, plan->err_flag + 2);
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
   RGNN_CHECK_CUDA(cudaFreeAsync(scratch, stream));
@@ -225,7 +239,7 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
   const size_t off_bytes = align_up(sizeof(int32_t) * ((size_t)num_nodes + 1), 256);
   const size_t m_bytes = align_up(sizeof(int32_t) * Mz, 256);
   plan->stream = stream;
-  PLAN_CUDA(cudaMallocAsync(&plan->block, off_bytes + 5 * m_bytes + 256, stream));
+  PLAN_CUDA(cudaMallocAsync(&plan->block, off_bytes + 5 * m_bytes + 256 + off_bytes, stream));
   {
     char* b = static_cast<char*>(plan->block);
     plan->seg_off = reinterpret_cast<int32_t*>(b);
@@ -235,11 +249,13 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
     plan->o_src = reinterpret_cast<int32_t*>(b + off_bytes + 3 * m_bytes);
     plan->o_tgt = reinterpret_cast<int32_t*>(b + off_bytes + 4 * m_bytes);
     plan->err_flag = reinterpret_cast<int*>(b + off_bytes + 5 * m_bytes);
+    plan->heavy_list = reinterpret_cast<int32_t*>(b + off_bytes + 5 * m_bytes + 256);
   }
-  PLAN_CUDA(cudaMemsetAsync(plan->err_flag, 0, sizeof(int), stream));
+  PLAN_CUDA(cudaMemsetAsync(plan->err_flag, 0, 4 * sizeof(int), stream));
 
   if (M == 0) {
     PLAN_CUDA(cudaMemsetAsync(plan->seg_off, 0, sizeof(int32_t) * ((size_t)num_nodes + 1), stream));
+    plan->num_heavy_host = 0;
     if (!deferred) PLAN_CUDA(cudaStreamSynchronize(stream));
     *out = plan;
     return RGNN_OK;
@@ -294,6 +310,12 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
     PLAN_CUDA2(cudaGetLastError());
     count_launch();
   }
+  if (num_nodes > 0) {
+    plan_heavy_kernel<<<(num_nodes + 255) / 256, 256, 0, stream>>>(plan->seg_off, num_nodes, RGNN_HEAVY_SEGMENT, plan->heavy_list,
+                                                                  plan->err_flag + 1);
+    PLAN_CUDA2(cudaGetLastError());
+    count_launch();
+  }
   PLAN_CUDA2(cudaFreeAsync(scratch, stream));
   if (!deferred) {
     const int rc = rgnn_plan_status(plan);
@@ -308,9 +330,11 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
 extern "C" int rgnn_plan_status(const rgnn_plan_t* plan) {
   RGNN_REQUIRE(plan != nullptr, "plan_status: plan is NULL");
   if (plan->err_flag == nullptr) return RGNN_OK;
-  int herr = 0;
-  RGNN_CHECK_CUDA(cudaMemcpyAsync(&herr, plan->err_flag, sizeof(int), cudaMemcpyDeviceToHost, plan->stream));
+  int flags[2] = {0, 0};
+  RGNN_CHECK_CUDA(cudaMemcpyAsync(flags, plan->err_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, plan->stream));
   RGNN_CHECK_CUDA(cudaStreamSynchronize(plan->stream));
+  const_cast<rgnn_plan*>(plan)->num_heavy_host = flags[1];
+  const int herr = flags[0];
   if (herr != 0) {
     set_error("plan: adjacency list holds a node index outside [0, %d)", plan->V);
     return RGNN_E_INVALID;

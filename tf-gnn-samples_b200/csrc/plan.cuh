@@ -23,7 +23,11 @@ struct rgnn_plan {
   int32_t* rev_src = nullptr;       // [M]
   int32_t* rev_type = nullptr;      // [M]
   void* rev_block = nullptr;
-  int* err_flag = nullptr;      // device flag: an adjacency list held an out-of-range node id
+  // targets with more than RGNN_HEAVY_SEGMENT incoming edges (reduced by a whole CTA, see seg_kernels.cu)
+  int32_t* heavy_list = nullptr;    // [V]
+  int32_t* rev_heavy_list = nullptr; // [V*L] (reverse index)
+  int num_heavy_host = -1;          // host copy of flags[1] once rgnn_plan_status has read it, else -1
+  int* err_flag = nullptr;          // device flags: [0] out-of-range node id seen, [1] number of heavy targets, [2] heavy (source,type) pairs      // device flag: an adjacency list held an out-of-range node id
   void* block = nullptr;        // the one pool allocation behind all arrays above
   cudaStream_t stream = nullptr; // creation stream (the block is freed stream-ordered on it)
 };
@@ -31,4 +35,5 @@ struct rgnn_plan {
 namespace rgnn {
 // Build plan->rev_* on `stream` if absent (not thread-safe; called by the first backward on this plan).
 int plan_ensure_reverse(rgnn_plan* plan, cudaStream_t stream);
+constexpr int RGNN_HEAVY_SEGMENT = 512;
 }  // namespace rgnn

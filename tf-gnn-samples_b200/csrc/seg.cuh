@@ -31,6 +31,12 @@ struct SegParams {
   const float* ln_beta = nullptr;
   float* out = nullptr;
   int ld_out = 0;
+  // degree-skew handling: targets with more than heavy_threshold incoming edges are skipped by the warp-per-target
+  // kernel and reduced by a whole CTA each (seg_reduce_heavy_kernel).  heavy_list / heavy_count live in the plan.
+  const int32_t* heavy_list = nullptr;
+  const int* heavy_count = nullptr;    // device counter
+  int heavy_threshold = 0;             // 0 = no splitting
+  int heavy_known = -1;                // host copy of *heavy_count, or -1 when it was never read back
 };
 int launch_seg_reduce(const SegParams& p, cudaStream_t stream);
 

@@ -71,28 +71,16 @@ __device__ __forceinline__ void warp_layer_norm(float4 (&x)[NV], const bool (&ok
 // above that size ran 1.5-2x slower at identical memory traffic (profiles/r01_seg_reduce_sweep.txt), so rare
 // paths are template flags (separate small kernels), not runtime branches, and nothing is duplicated.
 template <int NV, int MODE, bool MAXAGG, bool SCALED, bool ACTMSG>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const __grid_constant__ SegParams p) {
-  const int lane = threadIdx.x & 31;
-  const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (v >= p.V) return;
-  const int col0 = blockIdx.y * (128 * NV) + lane * 4;
-  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+__device__ __forceinline__ void seg_accumulate(const SegParams& p, int v, int col0, int lane, const bool (&ok)[NV],
+                                               int beg, int end, int chunk0, int chunk_stride, float4 (&acc)[NV]) {
   const int act_msg = ACTMSG ? p.act_msg : RGNN_ACT_LINEAR;
-
-  bool ok[NV];
-  float4 acc[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    ok[k] = (col0 + k * 128) < p.D;
-    acc[k] = f4(MAXAGG ? -FLT_MAX : 0.0f);   // empty max segment -> lowest() (A.2)
-  }
   int cur_type = -1;
   float4 m0[NV], m1[NV];   // gamma/beta (FILM) or q (ADDTGT) of the current (v, type) run
 #pragma unroll
   for (int k = 0; k < NV; ++k) { m0[k] = f4(1.0f); m1[k] = f4(0.0f); }
   const float* tbase = p.table + col0;
 
-  for (int e0 = beg; e0 < end; e0 += 32) {
+  for (int e0 = beg + 32 * chunk0; e0 < end; e0 += 32 * chunk_stride) {
     const int n = min(32, end - e0);
     int my_type = 0;
     float my_scale = 1.0f;
@@ -161,10 +149,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const 
       }
     }
   }
+}
 
-  // aggregation divisor (A.2): mean = sum / max(n,1); sqrt_n = sum / sqrt(max(n,1))
-  if (p.agg == RGNN_AGG_MEAN || p.agg == RGNN_AGG_SQRT_N) {
-    const float cnt = fmaxf((float)(end - beg), 1.0f);
+// aggregation divisor (A.2), output activation, optional layer norm, store
+template <int NV>
+__device__ __forceinline__ void seg_finish(const SegParams& p, int v, int col0, int lane, const bool (&ok)[NV], int count,
+                                           float4 (&acc)[NV]) {
+  if (p.agg == RGNN_AGG_MEAN || p.agg == RGNN_AGG_SQRT_N) {   // mean = sum / max(n,1); sqrt_n = sum / sqrt(max(n,1))
+    const float cnt = fmaxf((float)count, 1.0f);
     const float div = (p.agg == RGNN_AGG_MEAN) ? cnt : sqrtf(cnt);
 #pragma unroll
     for (int k = 0; k < NV; ++k)
@@ -177,6 +169,61 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const 
 #pragma unroll
   for (int k = 0; k < NV; ++k)
     if (ok[k]) *reinterpret_cast<float4*>(orow + k * 128) = acc[k];
+}
+
+template <int NV, int MODE, bool MAXAGG, bool SCALED, bool ACTMSG>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const __grid_constant__ SegParams p) {
+  const int lane = threadIdx.x & 31;
+  const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (v >= p.V) return;
+  const int col0 = blockIdx.y * (128 * NV) + lane * 4;
+  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  if (p.heavy_threshold > 0 && end - beg > p.heavy_threshold) return;   // left to seg_reduce_heavy_kernel
+  bool ok[NV];
+  float4 acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ok[k] = (col0 + k * 128) < p.D;
+    acc[k] = f4(MAXAGG ? -FLT_MAX : 0.0f);   // empty max segment -> lowest() (A.2)
+  }
+  seg_accumulate<NV, MODE, MAXAGG, SCALED, ACTMSG>(p, v, col0, lane, ok, beg, end, 0, 1, acc);
+  seg_finish<NV>(p, v, col0, lane, ok, end - beg, acc);
+}
+
+// Degree skew: a target with thousands of incoming edges would serialise on one warp (Zipf-skewed PPI-shaped
+// batch: 1.0 ms instead of 35 us per layer).  Here a whole CTA takes one heavy target: warp w reduces the
+// 32-edge chunks w, w+8, ..., the 8 partial rows are combined in a fixed order (still deterministic).
+template <int NV, int MODE, bool MAXAGG, bool SCALED, bool ACTMSG>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_heavy_kernel(const __grid_constant__ SegParams p) {
+  __shared__ float4 part[WARPS_PER_BLOCK][NV][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col0 = blockIdx.y * (128 * NV) + lane * 4;
+  const int nheavy = *p.heavy_count;
+  bool ok[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) ok[k] = (col0 + k * 128) < p.D;
+  for (int i = blockIdx.x; i < nheavy; i += gridDim.x) {
+    const int v = __ldg(p.heavy_list + i);
+    const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+    float4 acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = f4(MAXAGG ? -FLT_MAX : 0.0f);
+    seg_accumulate<NV, MODE, MAXAGG, SCALED, ACTMSG>(p, v, col0, lane, ok, beg, end, warp, WARPS_PER_BLOCK, acc);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) part[warp][k][lane] = acc[k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float4 t = part[0][k][lane];
+#pragma unroll
+        for (int w = 1; w < WARPS_PER_BLOCK; ++w) t = MAXAGG ? max4(t, part[w][k][lane]) : add4(t, part[w][k][lane]);
+        acc[k] = t;
+      }
+      seg_finish<NV>(p, v, col0, lane, ok, end - beg, acc);
+    }
+    __syncthreads();
+  }
 }
 
 // ---- RGAT: per-target, per-head online softmax fused with the weighted sum -----------------
@@ -451,10 +498,20 @@ static int seg_cols() {   // experiment knob: RGNN_SEG_COLS=256 -> one warp per 
   }
   return c;
 }
+template <int NV, int MODE, bool MAXAGG, bool SCALED, bool ACTMSG>
+static void launch_seg_pair(const SegParams& p, dim3 grid, cudaStream_t stream) {
+  seg_reduce_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  count_launch();
+  if (p.heavy_threshold > 0 && p.heavy_known != 0) {   // unknown (-1) or > 0: a few persistent CTAs walk the heavy list
+    const unsigned gx = p.heavy_known > 0 ? (unsigned)(p.heavy_known < 592 ? p.heavy_known : 592) : 148u;
+    seg_reduce_heavy_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG><<<dim3(gx, grid.y), WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+    count_launch();
+  }
+}
 template <int NV, int MODE, bool MAXAGG, bool SCALED>
 static void launch_seg_act(const SegParams& p, dim3 grid, cudaStream_t stream) {
-  if (p.act_msg != RGNN_ACT_LINEAR) seg_reduce_kernel<NV, MODE, MAXAGG, SCALED, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
-  else seg_reduce_kernel<NV, MODE, MAXAGG, SCALED, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  if (p.act_msg != RGNN_ACT_LINEAR) launch_seg_pair<NV, MODE, MAXAGG, SCALED, true>(p, grid, stream);
+  else launch_seg_pair<NV, MODE, MAXAGG, SCALED, false>(p, grid, stream);
 }
 template <int NV, int MODE, bool MAXAGG>
 static void launch_seg_scaled(const SegParams& p, dim3 grid, cudaStream_t stream) {
@@ -503,7 +560,6 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
     else launch_seg_nv<1>(p, dim3(gx, (p.D + 127) / 128), stream);
   }
   RGNN_CHECK_CUDA(cudaGetLastError());
-  count_launch();
   return RGNN_OK;
 }
 

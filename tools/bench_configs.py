@@ -44,7 +44,17 @@ def states(V, D, seed=1):
     return torch.as_tensor(np.tanh(np.random.default_rng(seed).standard_normal((V, D))).astype(np.float32)).to(dev)
 
 
-which = sys.argv[1:] or ["ggnn", "rgat", "film", "edge_mlp", "rgin", "rgcn5"]
+which = sys.argv[1:] or ["ggnn", "rgat", "film", "edge_mlp", "rgin", "rgcn5", "zipf"]
+if "zipf" in which:   # degree-skewed variant of config 2 (Zipf(1.0) targets): hubs with thousands of incoming edges
+    b = batching.ppi_like_batch(zipf_targets=True)
+    deg = b.type_to_num_incoming_edges.sum(axis=0)
+    h = states(b.num_nodes, 256)
+    cnt = torch.as_tensor(b.type_to_num_incoming_edges).to(dev)
+    plan = G.GraphPlan(b.adjacency_lists, b.num_nodes, device=dev)
+    w = W.to_torch(W.rgcn_weights(3, 256, 256), dev)
+    ms = timeit(lambda: G.sparse_rgcn_layer(h, plan, cnt, 256, activation_function="ReLU", weights=w))
+    report("RGCN PPI-shaped with Zipf(1.0) target skew (max in-degree %d, mean %.0f) hidden=256" % (int(deg.max()), float(deg.mean())),
+           b, 256, ms, 1, extra_bytes_per_edge=4)
 if "ggnn" in which:   # BASELINE config 3: GGNN QM9-shaped, 10k graphs, 4 bond types, hidden 128, 4 timesteps
     b = batching.qm9_like_batch(10000, seed=0)
     h = states(b.num_nodes, 128)
