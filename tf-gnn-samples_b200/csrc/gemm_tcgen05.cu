@@ -94,6 +94,28 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src
                : "memory");
 }
 
+__device__ __forceinline__ void bulk_copy_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                                        uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start>>4 | LBO | SBO=1024B | version 1 | layout 2.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -227,13 +249,16 @@ struct TcParams {
   int n_tiles;
   int tmem_cols;           // total allocation (two accumulators of tmem_cols/2 columns)
   int ring_bytes;
-  int total_tiles;
-  int tile_start[RGNN_MAX_EDGE_TYPES + 1];   // first tile of batch entry z (ROW_RANGES / COL_BLOCKS), else {0, total}
+  int total_tiles;         // number of tile GROUPS: a group = CL consecutive m-tiles x one n-tile, one per cluster step
+  int tile_start[RGNN_MAX_EDGE_TYPES + 1];   // first group of batch entry z (ROW_RANGES / COL_BLOCKS), else {0, total}
 };
 
 struct TileInfo { int z, m0, row_end, n_tile; };
 
-__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t) {
+// group t, CTA rank cr inside its cluster of CL: the m-tile is (group row) * CL + cr; it may lie past the last row
+// (dummy tile: loads are zero-filled, stores masked) so that every CTA of a cluster runs the same barrier protocol.
+template <int CL>
+__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t, int cr) {
   TileInfo ti;
   const GemmParams& g = p.g;
   int z = 0;
@@ -244,12 +269,15 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t) {
   const int row_begin = (g.batch_mode == BATCH_ROW_RANGES) ? g.row_off[z] : 0;
   ti.z = z;
   ti.row_end = (g.batch_mode == BATCH_ROW_RANGES) ? g.row_off[z + 1] : g.M;
-  ti.m0 = row_begin + (local / p.n_tiles) * TC_BM;
+  ti.m0 = row_begin + ((local / p.n_tiles) * CL + cr) * TC_BM;
   ti.n_tile = local % p.n_tiles;
   return ti;
 }
 
-template <int EPI>
+// CL = thread-block cluster size (1, 2 or 4).  The CL CTAs of a cluster work on CL consecutive m-tiles of the SAME
+// n-tile in lock step; each loads 1/CL of every weight-image chunk and TMA-multicasts it to all of them, so the
+// L2->SM traffic of B (the bound of this kernel, profiles/r01_gemm_tcgen05_timeline.txt) drops by CL.
+template <int EPI, int CL>
 __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const GemmParams& g = p.g;
@@ -265,12 +293,15 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   const uint32_t tfull0 = empty0 + 8 * S, tempty0 = tfull0 + 16;
   const uint32_t tmem_slot = tempty0 + 16;
   const int acc_cols = p.tmem_cols / 2;
-  const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+  const int cr = (CL > 1) ? (int)cluster_cta_rank() : 0;
+  const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+  const uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
+  const int my_tiles = (p.total_tiles - cid + ncl - 1) / ncl;   // tile groups of this cluster (same for its CTAs)
 
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, TC_GROUP_THREADS + 1);   // one producer group + the B loader's expect_tx arrival
-      mbar_init(empty0 + 8 * s, 1);                     // one tcgen05.commit
+      mbar_init(empty0 + 8 * s, CL);                    // one tcgen05.commit from every CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);                     // accumulator complete (tcgen05.commit)
@@ -285,6 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                       // every CTA's barriers are initialised before any remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = lds32(tmem_slot);
 
@@ -299,7 +331,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
     const int total_q = my_tiles * nchunks;
     auto load_a_chunk = [&](int q, float4 (&v)[8]) {
       const int ti_idx = q / nchunks, c = q - ti_idx * nchunks;
-      const TileInfo ti = decode_tile(p, (int)blockIdx.x + ti_idx * (int)gridDim.x);
+      const TileInfo ti = decode_tile<CL>(p, cid + ti_idx * ncl, cr);
       const bool seg2 = c >= p.chunks1;
       const int k0 = (seg2 ? c - p.chunks1 : c) * TC_BK;
       const int Kseg = seg2 ? g.K2 : g.K1;
@@ -364,7 +396,8 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
             umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
             umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1);
           }
-          umma_commit(empty0 + 8 * s);              // stage reusable once these MMAs have read it
+          if (CL > 1) umma_commit_multicast(empty0 + 8 * s, cl_mask);   // every CTA's loaders learn that this CTA is done with stage s
+          else umma_commit(empty0 + 8 * s);         // stage reusable once these MMAs have read it
         }
         umma_commit(tfull0 + 8 * a);                // accumulator complete -> epilogue
       }
@@ -375,15 +408,21 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
     if (lane == 0) {
       int q = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const TileInfo ti = decode_tile(p, (int)blockIdx.x + it * (int)gridDim.x);
+        const TileInfo ti = decode_tile<CL>(p, cid + it * ncl, cr);
         const float* src_tile = p.packed + (size_t)ti.z * p.packed_stride + (size_t)ti.n_tile * nchunks * 2 * (BN * TC_BK);
         for (int c = 0; c < nchunks; ++c, ++q) {
           const int s = q % S;
           const int use = q / S;
           if (use > 0) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
           const uint32_t b_hi = ring + (uint32_t)(s * stage_bytes + 2 * A_IMG_BYTES);
-          mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);
-          bulk_copy_g2s(b_hi, src_tile + (size_t)c * 2 * (BN * TC_BK), 2 * b_img_bytes, full0 + 8 * s);   // hi and lo are adjacent
+          mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);   // the whole chunk lands here, 1/CL from each CTA
+          if (CL > 1) {
+            const uint32_t part = (uint32_t)(2 * b_img_bytes) / CL;
+            bulk_copy_g2s_multicast(b_hi + cr * part, reinterpret_cast<const char*>(src_tile + (size_t)c * 2 * (BN * TC_BK)) + (size_t)cr * part,
+                                    part, full0 + 8 * s, cl_mask);
+          } else {
+            bulk_copy_g2s(b_hi, src_tile + (size_t)c * 2 * (BN * TC_BK), 2 * b_img_bytes, full0 + 8 * s);   // hi and lo are adjacent
+          }
         }
       }
     }
@@ -398,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
     const int dgru = (EPI == EPI_GRU_ZR) ? g.N / 2 : g.N;
     for (int it = 0; it < my_tiles; ++it) {
       const int a = it & 1;
-      const TileInfo ti = decode_tile(p, (int)blockIdx.x + it * (int)gridDim.x);
+      const TileInfo ti = decode_tile<CL>(p, cid + it * ncl, cr);
       float* C = g.C + (g.batch_mode == BATCH_COL_BLOCKS ? (size_t)ti.z * g.N : 0);
       const int n0 = ti.n_tile * BN;
       mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
@@ -464,6 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                       // no CTA leaves while peers may still multicast into it / arrive on it
   if (warp == MMA_WARP) {
     tc_fence_after_sync();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
@@ -553,19 +593,22 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   p.BN = pick_bn((rows + TC_BM - 1) / TC_BM, p.n_total, gz);
   const int n_tiles = (p.n_total + p.BN - 1) / p.BN;
   p.n_tiles = n_tiles;
-  // tile table: batch entry z owns tiles [tile_start[z], tile_start[z+1])
+  // cluster size: CTAs of a cluster share the weight images of one n-tile (TMA multicast)
+  static const int cl_env = getenv("RGNN_GEMM_CLUSTER") ? atoi(getenv("RGNN_GEMM_CLUSTER")) : 0;
+  const int m_tiles_all = (rows + TC_BM - 1) / TC_BM;
+  int CL = m_tiles_all >= 64 ? 4 : (m_tiles_all >= 4 ? 2 : 1);
+  if (cl_env == 1 || cl_env == 2 || cl_env == 4) CL = cl_env;
+  auto groups_of = [&](int nrows) { return (((nrows + TC_BM - 1) / TC_BM + CL - 1) / CL) * n_tiles; };
+  // group table: batch entry z owns groups [tile_start[z], tile_start[z+1])
   p.tile_start[0] = 0;
   if (g.batch_mode == BATCH_ROW_RANGES) {
-    for (int z = 0; z < g.batch; ++z) {
-      const int rz = g.row_off[z + 1] - g.row_off[z];
-      p.tile_start[z + 1] = p.tile_start[z] + ((rz + TC_BM - 1) / TC_BM) * n_tiles;
-    }
+    for (int z = 0; z < g.batch; ++z) p.tile_start[z + 1] = p.tile_start[z] + groups_of(g.row_off[z + 1] - g.row_off[z]);
     p.total_tiles = p.tile_start[g.batch];
   } else if (g.batch_mode == BATCH_COL_BLOCKS) {
-    for (int z = 0; z < g.batch; ++z) p.tile_start[z + 1] = p.tile_start[z] + ((g.M + TC_BM - 1) / TC_BM) * n_tiles;
+    for (int z = 0; z < g.batch; ++z) p.tile_start[z + 1] = p.tile_start[z] + groups_of(g.M);
     p.total_tiles = p.tile_start[g.batch];
   } else {
-    p.total_tiles = ((g.M + TC_BM - 1) / TC_BM) * n_tiles;
+    p.total_tiles = groups_of(g.M);
     p.tile_start[1] = p.total_tiles;
   }
   if (p.total_tiles <= 0) return RGNN_OK;
@@ -630,13 +673,6 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   }
 
   const size_t smem = 1024 + (size_t)p.ring_bytes + EPI_STAGE_BYTES + (2 * p.stages + 4) * sizeof(uint64_t) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
-    RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI_GRU_ZR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
-    RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI_GRU_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
-    attr_set = true;
-  }
   static int num_sms = 0;
   if (num_sms == 0) {
     int device = 0;
@@ -644,12 +680,50 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
     if (num_sms <= 0) num_sms = 148;
   }
-  const dim3 grid(p.total_tiles < num_sms ? p.total_tiles : num_sms);   // persistent: at most one CTA per SM
-  switch (g.epi) {
-    case EPI_GRU_ZR: gemm_tcgen05_kernel<EPI_GRU_ZR><<<grid, TC_THREADS_V4, smem, stream>>>(p); break;
-    case EPI_GRU_OUT: gemm_tcgen05_kernel<EPI_GRU_OUT><<<grid, TC_THREADS_V4, smem, stream>>>(p); break;
-    default: gemm_tcgen05_kernel<EPI_STORE><<<grid, TC_THREADS_V4, smem, stream>>>(p); break;
+  int max_clusters = num_sms / CL;
+
+  using KernelFn = void (*)(TcParams);
+  auto pick = [&](int epi) -> KernelFn {
+    switch (epi * 8 + CL) {
+      case EPI_STORE * 8 + 1: return gemm_tcgen05_kernel<EPI_STORE, 1>;
+      case EPI_STORE * 8 + 2: return gemm_tcgen05_kernel<EPI_STORE, 2>;
+      case EPI_STORE * 8 + 4: return gemm_tcgen05_kernel<EPI_STORE, 4>;
+      case EPI_GRU_ZR * 8 + 1: return gemm_tcgen05_kernel<EPI_GRU_ZR, 1>;
+      case EPI_GRU_ZR * 8 + 2: return gemm_tcgen05_kernel<EPI_GRU_ZR, 2>;
+      case EPI_GRU_ZR * 8 + 4: return gemm_tcgen05_kernel<EPI_GRU_ZR, 4>;
+      case EPI_GRU_OUT * 8 + 1: return gemm_tcgen05_kernel<EPI_GRU_OUT, 1>;
+      case EPI_GRU_OUT * 8 + 2: return gemm_tcgen05_kernel<EPI_GRU_OUT, 2>;
+      default: return gemm_tcgen05_kernel<EPI_GRU_OUT, 4>;
+    }
+  };
+  KernelFn fn = pick(g.epi);
+  static bool attr_done[3][5] = {};
+  if (!attr_done[g.epi][CL]) {
+    RGNN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+    attr_done[g.epi][CL] = true;
   }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TC_THREADS_V4);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (CL > 1) {   // clusters of 4 cannot use every SM (GPC sizes): size the persistent grid by what is co-resident
+    static int cached[3][5] = {};
+    if (cached[g.epi][CL] == 0) {
+      cfg.gridDim = dim3((unsigned)(max_clusters * CL));
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) == cudaSuccess && n > 0) cached[g.epi][CL] = n;
+      else { cudaGetLastError(); cached[g.epi][CL] = max_clusters; }
+    }
+    if (cached[g.epi][CL] < max_clusters) max_clusters = cached[g.epi][CL];
+  }
+  const int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;   // persistent: at most one CTA per SM
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  RGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return RGNN_OK;
