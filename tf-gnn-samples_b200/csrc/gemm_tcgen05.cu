@@ -596,7 +596,11 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   // cluster size: CTAs of a cluster share the weight images of one n-tile (TMA multicast)
   static const int cl_env = getenv("RGNN_GEMM_CLUSTER") ? atoi(getenv("RGNN_GEMM_CLUSTER")) : 0;
   const int m_tiles_all = (rows + TC_BM - 1) / TC_BM;
-  int CL = m_tiles_all >= 64 ? 4 : (m_tiles_all >= 4 ? 2 : 1);
+  // Measured on B200 (profiles/r01_gemm_cluster_sweep.txt): multicasting the weight images over clusters of 2 / 4 does not
+  // speed this kernel up -- the bound is what each SM can ingest (~30 B/clk) and feed to the tensor core from its own
+  // shared memory, not the L2 read traffic -- so the default stays 1; RGNN_GEMM_CLUSTER=2|4 keeps the path testable.
+  (void)m_tiles_all;
+  int CL = 1;
   if (cl_env == 1 || cl_env == 2 || cl_env == 4) CL = cl_env;
   auto groups_of = [&](int nrows) { return (((nrows + TC_BM - 1) / TC_BM + CL - 1) / CL) * n_tiles; };
   // group table: batch entry z owns groups [tile_start[z], tile_start[z+1])
