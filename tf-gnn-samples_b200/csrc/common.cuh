@@ -47,9 +47,16 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // (4 components x rows in flight x 2 sites) made the first segment kernel 26k SASS instructions and
 // instruction-fetch bound (profiles/r01_seg_reduce_v1.txt).  relu / linear / leaky_relu stay inline.
 // Each translation unit gets its own copy (static), so no relocatable device code is needed.
+// tanh is the default activation of GGNN / RGAT / the scaffold and sits in GEMM epilogues (GRU candidate state):
+// 1 - 2 / (exp(2x) + 1) with the SFU exponential -- absolute error < 1e-6 (the parity metric is max-norm, 1e-4),
+// exact limits at +-inf, 6 instructions instead of the ~40 of tanhf (the GRU output GEMM was epilogue-bound on it).
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
 static __device__ __noinline__ float slow_act(float x, int act) {
   switch (act) {
-    case RGNN_ACT_TANH: return tanhf(x);
+    case RGNN_ACT_TANH: return fast_tanh(x);
     case RGNN_ACT_ELU: return x > 0.0f ? x : expm1f(x);
     case RGNN_ACT_SELU: return 1.0507009873554805f * (x > 0.0f ? x : 1.6732632423543772f * expm1f(x));
     case RGNN_ACT_GELU: return x * (0.5f * (1.0f + erff(x * 0.70710678118654752f)));  // exact-erf form
@@ -60,6 +67,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == RGNN_ACT_LINEAR) return x;
   if (act == RGNN_ACT_RELU) return fmaxf(x, 0.0f);
   if (act == RGNN_ACT_LEAKY_RELU) return x > 0.0f ? x : 0.2f * x;        // tf.nn.leaky_relu alpha=0.2
+  if (act == RGNN_ACT_TANH) return fast_tanh(x);
   return slow_act(x, act);
 }
 __device__ __forceinline__ float hard_sigmoid(float x) {                 // Keras hard_sigmoid (TF1 GRU default)
@@ -67,7 +75,6 @@ __device__ __forceinline__ float hard_sigmoid(float x) {                 // Kera
 }
 static __device__ __noinline__ float4 slow_act4(float4 v, int act) {     // one call per 4 elements
   switch (act) {
-    case RGNN_ACT_TANH: return make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
     case RGNN_ACT_GELU:
       return make_float4(v.x * (0.5f * (1.0f + erff(v.x * 0.70710678118654752f))), v.y * (0.5f * (1.0f + erff(v.y * 0.70710678118654752f))),
                          v.z * (0.5f * (1.0f + erff(v.z * 0.70710678118654752f))), v.w * (0.5f * (1.0f + erff(v.w * 0.70710678118654752f))));
@@ -80,6 +87,7 @@ __device__ __forceinline__ float4 act4(float4 v, int act) {
   if (act == RGNN_ACT_LEAKY_RELU)
     return make_float4(v.x > 0.0f ? v.x : 0.2f * v.x, v.y > 0.0f ? v.y : 0.2f * v.y, v.z > 0.0f ? v.z : 0.2f * v.z,
                        v.w > 0.0f ? v.w : 0.2f * v.w);
+  if (act == RGNN_ACT_TANH) return make_float4(fast_tanh(v.x), fast_tanh(v.y), fast_tanh(v.z), fast_tanh(v.w));
   return slow_act4(v, act);
 }
 
