@@ -73,21 +73,29 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 __device__ __forceinline__ float hard_sigmoid(float x) {                 // Keras hard_sigmoid (TF1 GRU default)
   return fminf(fmaxf(0.2f * x + 0.5f, 0.0f), 1.0f);
 }
-static __device__ __noinline__ float4 slow_act4(float4 v, int act) {     // one call per 4 elements
+static __device__ __noinline__ float4 slow_act4(float4 v, int act) {     // one call per 4 elements, every activation
   switch (act) {
+    case RGNN_ACT_RELU: return make_float4(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f), fmaxf(v.z, 0.0f), fmaxf(v.w, 0.0f));
+    case RGNN_ACT_TANH: return make_float4(fast_tanh(v.x), fast_tanh(v.y), fast_tanh(v.z), fast_tanh(v.w));
+    case RGNN_ACT_LEAKY_RELU:
+      return make_float4(v.x > 0.0f ? v.x : 0.2f * v.x, v.y > 0.0f ? v.y : 0.2f * v.y, v.z > 0.0f ? v.z : 0.2f * v.z,
+                         v.w > 0.0f ? v.w : 0.2f * v.w);
     case RGNN_ACT_GELU:
       return make_float4(v.x * (0.5f * (1.0f + erff(v.x * 0.70710678118654752f))), v.y * (0.5f * (1.0f + erff(v.y * 0.70710678118654752f))),
                          v.z * (0.5f * (1.0f + erff(v.z * 0.70710678118654752f))), v.w * (0.5f * (1.0f + erff(v.w * 0.70710678118654752f))));
     default: return make_float4(slow_act(v.x, act), slow_act(v.y, act), slow_act(v.z, act), slow_act(v.w, act));
   }
 }
+// Hot per-message path: linear / relu inline, everything else one out-of-line call per float4.
 __device__ __forceinline__ float4 act4(float4 v, int act) {
   if (act == RGNN_ACT_LINEAR) return v;
   if (act == RGNN_ACT_RELU) return make_float4(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f), fmaxf(v.z, 0.0f), fmaxf(v.w, 0.0f));
-  if (act == RGNN_ACT_LEAKY_RELU)
-    return make_float4(v.x > 0.0f ? v.x : 0.2f * v.x, v.y > 0.0f ? v.y : 0.2f * v.y, v.z > 0.0f ? v.z : 0.2f * v.z,
-                       v.w > 0.0f ? v.w : 0.2f * v.w);
-  if (act == RGNN_ACT_TANH) return make_float4(fast_tanh(v.x), fast_tanh(v.y), fast_tanh(v.z), fast_tanh(v.w));
+  return slow_act4(v, act);
+}
+// Cold path (row epilogues, GEMM epilogue): nothing inline -- these kernels must stay under the ~2048-instruction
+// L1.5 I-cache (inlining tanh into the 8x-unrolled GEMM epilogue grew it to 2360 and cost 40 % on the FiLM config).
+__device__ __forceinline__ float4 act4_cold(float4 v, int act) {
+  if (act == RGNN_ACT_LINEAR) return v;
   return slow_act4(v, act);
 }
 

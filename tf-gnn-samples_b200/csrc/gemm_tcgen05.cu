@@ -258,7 +258,7 @@ struct TileInfo { int z, m0, row_end, n_tile; };
 // group t, CTA rank cr inside its cluster of CL: the m-tile is (group row) * CL + cr; it may lie past the last row
 // (dummy tile: loads are zero-filled, stores masked) so that every CTA of a cluster runs the same barrier protocol.
 template <int CL>
-__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t, int cr) {
+__device__ __noinline__ TileInfo decode_tile(const TcParams& p, int t, int cr) {   // once per tile and role: keep it out of line (I-cache)
   TileInfo ti;
   const GemmParams& g = p.g;
   int z = 0;
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
           if (r < ti.row_end && col_ok) {
             float4 x = make_float4(o[j].x + bias4.x, o[j].y + bias4.y, o[j].z + bias4.z, o[j].w + bias4.w);
             if (EPI == EPI_STORE) {
-              x = act4(x, g.act);
+              x = act4_cold(x, g.act);
               *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = x;
             } else if (EPI == EPI_GRU_ZR) {
               x.x = hard_sigmoid(x.x); x.y = hard_sigmoid(x.y); x.z = hard_sigmoid(x.z); x.w = hard_sigmoid(x.w);
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
                 *reinterpret_cast<float4*>(g.C2 + (size_t)r * g.ldc2 + cc) = make_float4(x.x * h.x, x.y * h.y, x.z * h.z, x.w * h.w);
               }
             } else {  // EPI_GRU_OUT: h' = z*h + (1-z)*act(.)
-              x = act4(x, g.act);
+              x = act4_cold(x, g.act);
               const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + c));
               const float4 zz = __ldg(reinterpret_cast<const float4*>(g.aux_z + (size_t)r * g.ld_z + c));
               *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) =
@@ -714,7 +714,7 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (CL > 1) ? 1 : 0;   // plain launch when there is no cluster
   if (CL > 1) {   // clusters of 4 cannot use every SM (GPC sizes): size the persistent grid by what is co-resident
     static int cached[3][5] = {};
     if (cached[g.epi][CL] == 0) {

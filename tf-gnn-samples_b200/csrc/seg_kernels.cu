@@ -163,7 +163,7 @@ __device__ __forceinline__ void seg_finish(const SegParams& p, int v, int col0, 
       acc[k] = make_float4(acc[k].x / div, acc[k].y / div, acc[k].z / div, acc[k].w / div);
   }
 #pragma unroll
-  for (int k = 0; k < NV; ++k) acc[k] = act4(acc[k], p.act_out);
+  for (int k = 0; k < NV; ++k) acc[k] = act4_cold(acc[k], p.act_out);
   if (p.ln_gamma != nullptr) warp_layer_norm<NV>(acc, ok, p.D, lane, p.ln_gamma, p.ln_beta);
   float* orow = p.out + (size_t)v * p.ld_out + col0;
 #pragma unroll
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __
     if (ok[k]) {
       float4 o = f4(0.0f);                                    // no incoming message -> zeros (A.7)
       if (end > beg) o = make_float4(acc[k].x / den[k], acc[k].y / den[k], acc[k].z / den[k], acc[k].w / den[k]);
-      *reinterpret_cast<float4*>(orow + k * 128) = act4(o, p.act_out);
+      *reinterpret_cast<float4*>(orow + k * 128) = act4_cold(o, p.act_out);
     }
 }
 
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) edge_build_kernel(const 
   } else {
     const float* qrow = p.q + (size_t)tgt * p.q_stride_node + (size_t)l * p.q_stride_type;
     for (int c = lane * 4; c < p.D; c += 128)
-      *reinterpret_cast<float4*>(xrow + c) = act4(add4(ldg4(prow + c), ldg4(qrow + c)), p.act);
+      *reinterpret_cast<float4*>(xrow + c) = act4_cold(add4(ldg4(prow + c), ldg4(qrow + c)), p.act);
   }
 }
 
