@@ -206,6 +206,11 @@ RGNN_API int rgnn_segment_aggregate(const rgnn_plan_t* plan, const float* data, 
  * (fp32-accurate); the node-level Dense of every layer (A.1). bias may be NULL. */
 RGNN_API int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const float* b, int32_t n,
                        const float* bias, int activation, float* c, void* stream);
+/* Gradients of the linear map C = A . B: grad_a [M,K] = grad_c . B^T, grad_b [K,N] = A^T . grad_c (split-K on the tensor
+ * cores, deterministic).  Either output may be NULL.  The reference gets these from TF autodiff of its Dense kernels
+ * (models/sparse_graph_model.py:253-260). */
+RGNN_API int rgnn_dense_backward(const float* a, int32_t m, int32_t k, const float* b, int32_t n, const float* grad_c,
+                        float* grad_a, float* grad_b, void* stream);
 /* tf.contrib.layers.layer_norm over the last axis, eps 1e-12 (A.5). */
 RGNN_API int rgnn_layer_norm(const float* x, int32_t rows, int32_t d, const float* gamma, const float* beta,
                     float* out, void* stream);

@@ -39,6 +39,43 @@ def test_dense_bias_activation(cuda_device):
         assert_parity(got, want, "dense+bias+%s" % act, tol=1e-5)
 
 
+# (rows m = the long contraction axis of the weight gradient, k = in, n = out)
+@pytest.mark.parametrize("m,k,n", [(1, 4, 4), (31, 8, 12), (33, 132, 260), (2245, 256, 768), (11225, 256, 256),
+                                   (5000, 52, 124), (70000, 128, 128), (97, 512, 36)])
+def test_dense_backward_matches_fp64(cuda_device, m, k, n):
+    """grad_x = g . W^T (transposed-weight tcgen05 GEMM) and grad_W = x^T . g (split-K TN kernel) against float64."""
+    import torch
+    rng = np.random.default_rng(m + 3 * k + n)
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    g = rng.standard_normal((m, n)).astype(np.float32)
+    gx, gw = ops.dense_backward(torch.as_tensor(x).to(cuda_device), torch.as_tensor(w).to(cuda_device),
+                                torch.as_tensor(g).to(cuda_device))
+    assert_parity(gx.cpu().numpy(), g.astype(np.float64) @ w.astype(np.float64).T, "dense grad_x %dx%dx%d" % (m, k, n), tol=1e-5)
+    err = assert_parity(gw.cpu().numpy(), x.astype(np.float64).T @ g.astype(np.float64), "dense grad_w %dx%dx%d" % (m, k, n), tol=1e-5)
+    print("dense grad_w %dx%dx%d max-norm rel err %.2e" % (m, k, n, err))
+    # deterministic: the split-K partial sums are combined in a fixed order
+    _, gw2 = ops.dense_backward(torch.as_tensor(x).to(cuda_device), torch.as_tensor(w).to(cuda_device),
+                                torch.as_tensor(g).to(cuda_device), need_x=False)
+    assert torch.equal(gw, gw2)
+
+
+def test_dense_autograd(cuda_device):
+    """ops.dense under autograd: tanh(x W + b) gradients against torch float64 on the CPU."""
+    import torch
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((301, 48)).astype(np.float32)
+    w = (rng.standard_normal((48, 40)) / 7).astype(np.float32)
+    b = rng.standard_normal(40).astype(np.float32)
+    c = rng.standard_normal((301, 40)).astype(np.float32)
+    td = [torch.as_tensor(a).to(cuda_device).requires_grad_(True) for a in (x, w, b)]
+    (ops.dense(td[0], td[1], td[2], "tanh") * torch.as_tensor(c).to(cuda_device)).sum().backward()
+    t64 = [torch.as_tensor(a, dtype=torch.float64).requires_grad_(True) for a in (x, w, b)]
+    (torch.tanh(t64[0] @ t64[1] + t64[2]) * torch.as_tensor(c, dtype=torch.float64)).sum().backward()
+    for got, want, name in zip(td, t64, ["x", "kernel", "bias"]):
+        assert_parity(got.grad.cpu().numpy(), want.grad.numpy(), "dense autograd d%s" % name, tol=2e-5)
+
+
 @pytest.mark.parametrize("agg", ["sum", "max", "mean", "sqrt_n"])
 def test_segment_aggregate(cuda_device, agg):
     import torch

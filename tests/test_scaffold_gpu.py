@@ -55,3 +55,66 @@ def test_training_steps_reduce_the_loss(cuda_device):
     assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0], losses
     for p in model.edge_weights:                                   # the engine's backward reached every GNN kernel
         assert p.grad is not None and float(p.grad.abs().max()) > 0
+
+
+def test_whole_model_gradients_match_float64(cuda_device):
+    """d loss / d parameter through the engine (RGCN backward kernels + tensor-core Dense gradients) against the same
+    model written in plain torch float64 on the CPU with autograd (reference op order: gather -> per-edge matmul ->
+    scale -> scatter-add, gnns/rgcn.py:84-114).  The GNN activation is tanh here: with the default ReLU an fp32 / fp64
+    sign disagreement on ONE pre-activation of ~1e-6 (about one per 100k elements at fp32 accuracy) switches a whole
+    gradient path on or off and shows up as a percent-level max-norm difference that says nothing about the kernels;
+    ReLU' itself is covered per layer in test_backward_gpu.py."""
+    import torch
+    b = batching.ppi_like_batch(num_nodes=400, num_links=5000, seed=21)
+    model = RGCNPPIModel(device=cuda_device, params={"graph_activation_function": "tanh"})
+    feats = torch.as_tensor(b.node_features).to(cuda_device)
+    cnt = torch.as_tensor(b.type_to_num_incoming_edges).to(cuda_device)
+    plan = GraphPlan(b.adjacency_lists, b.num_nodes, device=cuda_device)
+    labels = (torch.rand((b.num_nodes, 121), generator=torch.Generator().manual_seed(5)) < 0.3).float()
+    model.train()
+    m = model.task_metrics(model(feats, plan, cnt), labels.to(cuda_device))
+    m["loss"].backward()
+
+    # float64 restatement
+    P = {n: p.detach().cpu().double().requires_grad_(True) for n, p in model.named_parameters()}
+    x = torch.as_tensor(b.node_features, dtype=torch.float64)
+    c = torch.as_tensor(b.type_to_num_incoming_edges, dtype=torch.float64)
+    cur = torch.tanh(x @ P["projection"])
+    L = model.num_edge_types
+    for l in range(model.params["graph_num_layers"]):
+        msgs, tgts = [], []
+        for t, a in enumerate(b.adjacency_lists):
+            a = torch.as_tensor(np.asarray(a), dtype=torch.long).reshape(-1, 2)
+            msg = cur[a[:, 0]] @ P["edge_weights.%d" % (l * L + t)]
+            msgs.append(msg * (1.0 / (c[t][a[:, 1]] + 1e-7)).unsqueeze(-1))
+            tgts.append(a[:, 1])
+        agg = torch.zeros((b.num_nodes, 256), dtype=torch.float64).index_add_(0, torch.cat(tgts), torch.cat(msgs))
+        cur = torch.tanh(agg)
+        if str(l) in model.inter_dense:
+            cur = torch.tanh(cur @ P["inter_dense.%d" % l])
+    logits = cur @ P["out_kernel"] + P["out_bias"]
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels.double(), reduction="sum") / b.num_nodes
+    loss.backward()
+    assert abs(float(m["loss"].detach()) - float(loss.detach())) < 1e-4 * abs(float(loss))
+    errs = {}
+    for n, p in model.named_parameters():
+        got, want = p.grad.cpu().numpy().astype(np.float64), P[n].grad.numpy()
+        errs[n] = float(np.abs(got - want).max() / np.abs(want).max())
+    print("whole-model gradient max-norm rel errors:", {k: "%.2e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 2e-4, errs
+
+
+def test_train_step_async_matches_manual_clip(cuda_device):
+    """clip_gradients_ is tf.clip_by_norm per tensor: g * clip / max(||g||, clip)."""
+    import torch
+    model = RGCNPPIModel(device=cuda_device, params={"clamp_gradient_norm": 0.5})
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    want = []
+    for i, q in enumerate(model.parameters()):
+        g = torch.randn(q.shape, generator=gen) * (0.001 if i % 2 else 1.0)      # some below, some above the threshold
+        q.grad = g.to(cuda_device)
+        n = float(g.double().norm())
+        want.append((g.double() * 0.5 / max(n, 0.5)).numpy())
+    model.clip_gradients_()
+    for q, w in zip(model.parameters(), want):
+        assert_parity(q.grad.cpu().numpy(), w, "clip_by_norm", tol=1e-6)

@@ -59,6 +59,18 @@ void gemm_weight_cache_enable(bool on);
 void gemm_weight_cache_clear();
 bool gemm_weight_cache_enabled();
 
+// C[M, N] = A^T . B, A [K, M] (lda), B [K, N] (ldb), K long (gemm_tn_tcgen05.cu): split-K over one wave of CTAs,
+// deterministic two-stage sum.  The result is written as N / block_cols column blocks, block b to ptr[b] (row
+// stride ld) -- one block per edge type for the per-type kernels' gradients.
+struct GemmTnOut {
+  float* ptr[RGNN_MAX_EDGE_TYPES];
+  int block_cols = 0;
+  int ld = 0;
+};
+size_t gemm_tn_scratch_floats(int M, int N, int K);
+int launch_gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const GemmTnOut& out,
+                   float* scratch, cudaStream_t stream);
+
 // true unless the environment says RGNN_GEMM_IMPL=mma
 bool gemm_use_tcgen05();
 

@@ -272,7 +272,7 @@ extern "C" size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, 
     case RGNN_LAYER_GGNN: floats = V * L * dm + 6 * V * dm; break;
     case RGNN_LAYER_RGAT: floats = V * L * dm + 2 * V * L * dm / 4 + 2 * V * dm; break;
     case RGNN_LAYER_FILM: floats = 3 * V * L * dm + 2 * V * dm; break;
-    case RGNN_LAYER_RGCN_BACKWARD: floats = 2 * V * L * dm + 2 * V * dm + 64 * L * dm * dm + 64 * 1024; break;
+    case RGNN_LAYER_RGCN_BACKWARD: floats = 2 * V * L * dm + 2 * V * dm + (148 * 16384 + L * dm * dm) + 64 * 1024; break;   // + split-K partial tiles of dW
     case RGNN_LAYER_EDGE_MLP:
     case RGNN_LAYER_RGIN: {
       const size_t nl = (size_t)(mlp_layers > 0 ? mlp_layers : 1);
@@ -367,7 +367,9 @@ extern "C" int rgnn_rgcn_backward(const rgnn_plan_t* plan_c, const float* h, int
     pre = ar.floats((size_t)V * d_out);
     t_fwd = ar.floats((size_t)V * L * d_out);
   }
-  float* gw_scratch = grad_edge_weights ? ar.floats(grad_weight_scratch_floats(V, L, d_in, d_out)) : nullptr;
+  static const bool gradw_fma = getenv("RGNN_GRADW_IMPL") != nullptr && strcmp(getenv("RGNN_GRADW_IMPL"), "fma") == 0;   // A/B reference
+  float* gw_scratch = nullptr;
+  if (grad_edge_weights) gw_scratch = ar.floats(gradw_fma ? grad_weight_scratch_floats(V, L, d_in, d_out) : gemm_tn_scratch_floats(d_in, L * d_out, V));
   RGNN_PROPAGATE(check_ws(ar, "rgcn_backward"));
 
   if (pre != nullptr) {
@@ -400,12 +402,17 @@ extern "C" int rgnn_rgcn_backward(const rgnn_plan_t* plan_c, const float* h, int
     RGNN_PROPAGATE(run_gemm(g, ar, stream));
   }
   if (grad_edge_weights != nullptr) {
+    // dW_l = H^T . dT[:, l, :]  -- one TN contraction over the V nodes for all types (gemm_tn_tcgen05.cu)
     GradWTable tab;
+    GemmTnOut tn;
+    tn.block_cols = d_out; tn.ld = d_out;
     for (int l = 0; l < L; ++l) {
       RGNN_REQUIRE(grad_edge_weights[l] != nullptr && aligned16(grad_edge_weights[l]), "rgcn_backward: grad weight %d is NULL / misaligned", l);
       tab.out[l] = grad_edge_weights[l];
+      tn.ptr[l] = grad_edge_weights[l];
     }
-    RGNN_PROPAGATE(launch_grad_weights(h, d_t, V, L, d_in, d_out, tab, gw_scratch, stream));
+    if (gradw_fma) RGNN_PROPAGATE(launch_grad_weights(h, d_t, V, L, d_in, d_out, tab, gw_scratch, stream));
+    else RGNN_PROPAGATE(launch_gemm_tn(h, d_in, d_t, L * d_out, d_in, L * d_out, V, tn, gw_scratch, stream));
   }
   return RGNN_OK;
 }
@@ -730,6 +737,37 @@ extern "C" int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const fl
   const int rc = launch_gemm_tcgen05(g, ws, need, stream);
   cudaFreeAsync(ws, stream);
   return rc;
+}
+
+// gradients of the linear map C = A . B of rgnn_dense_forward (TF autodiff of tf.keras Dense, sparse_graph_model.py:253)
+extern "C" int rgnn_dense_backward(const float* a, int32_t m, int32_t k, const float* b, int32_t n, const float* grad_c,
+                                   float* grad_a, float* grad_b, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_REQUIRE(grad_c != nullptr && m >= 0 && k > 0 && n > 0 && (k % 4) == 0 && (n % 4) == 0, "dense_backward: bad arguments (m=%d k=%d n=%d)", m, k, n);
+  RGNN_REQUIRE(gemm_use_tcgen05(), "dense_backward needs the tcgen05 GEMM (unset RGNN_GEMM_IMPL=mma)");
+  if (grad_a != nullptr && m > 0) {   // dA = dC . B^T
+    RGNN_REQUIRE(b != nullptr, "dense_backward: grad_a needs b");
+    GemmParams g;
+    g.A1 = grad_c; g.lda1 = n; g.K1 = n; g.M = m; g.N = k; g.C = grad_a; g.ldc = k; g.ldb1 = n;
+    g.batch_mode = BATCH_K_BLOCKS_T; g.batch = 1; g.k_block = n; g.bptr[0] = b; g.bptr2[0] = nullptr;
+    const size_t need = gemm_tc_pack_bytes(g);
+    void* ws = nullptr;
+    RGNN_CHECK_CUDA(cudaMallocAsync(&ws, need, stream));
+    const int rc = launch_gemm_tcgen05(g, ws, need, stream);
+    cudaFreeAsync(ws, stream);
+    RGNN_PROPAGATE(rc);
+  }
+  if (grad_b != nullptr) {            // dB = A^T . dC
+    RGNN_REQUIRE(a != nullptr || m == 0, "dense_backward: grad_b needs a");
+    GemmTnOut tn;
+    tn.block_cols = n; tn.ld = n; tn.ptr[0] = grad_b;
+    void* ws = nullptr;
+    RGNN_CHECK_CUDA(cudaMallocAsync(&ws, gemm_tn_scratch_floats(k, n, m) * sizeof(float), stream));
+    const int rc = launch_gemm_tn(a, k, grad_c, n, k, n, m, tn, static_cast<float*>(ws), stream);
+    cudaFreeAsync(ws, stream);
+    RGNN_PROPAGATE(rc);
+  }
+  return RGNN_OK;
 }
 
 extern "C" int rgnn_layer_norm(const float* x, int32_t rows, int32_t d, const float* gamma, const float* beta,

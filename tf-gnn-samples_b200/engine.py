@@ -61,6 +61,7 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_int, _PTR, _PTR, c_size_t, _PTR]),
     "rgnn_segment_aggregate": (c_int, [_PTR, _PTR, c_int32, c_int, _PTR, _PTR]),
     "rgnn_dense_forward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
+    "rgnn_dense_backward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, _PTR, _PTR, _PTR]),
     "rgnn_layer_norm": (c_int, [_PTR, c_int32, c_int32, _PTR, _PTR, _PTR, _PTR]),
     "rgnn_rgcn_stack_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int,
                                         _PTR, _PTR, c_size_t, _PTR]),

@@ -6,22 +6,73 @@ import torch
 
 from .engine import GraphPlan, RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, load_library
 from .utils import get_activation, get_aggregation_function
+from .utils import (ACT_ELU, ACT_GELU, ACT_LEAKY_RELU, ACT_LINEAR, ACT_RELU, ACT_SELU, ACT_TANH)
+
+# torch spellings of utils/utils.py:36-58 for the differentiable paths
+_TORCH_ACT = {
+    ACT_LINEAR: lambda t: t, ACT_TANH: torch.tanh, ACT_RELU: torch.relu,
+    ACT_LEAKY_RELU: lambda t: torch.nn.functional.leaky_relu(t, 0.2), ACT_ELU: torch.nn.functional.elu,
+    ACT_SELU: torch.selu, ACT_GELU: lambda t: torch.nn.functional.gelu(t),
+}
+
+
+def _dense_raw(x, kernel, b, act_code):
+    out = torch.empty((x.shape[0], kernel.shape[1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load_library().rgnn_dense_forward(x.data_ptr(), x.shape[0], x.shape[1], kernel.data_ptr(), kernel.shape[1],
+                                                b.data_ptr() if b is not None else None, act_code,
+                                                out.data_ptr(), current_stream_ptr(x.device)))
+    return out
+
+
+def dense_backward(x: torch.Tensor, kernel: torch.Tensor, grad_out: torch.Tensor, need_x: bool = True,
+                   need_kernel: bool = True):
+    """Gradients of y = x @ kernel: (grad_out @ kernel^T, x^T @ grad_out) through rgnn_dense_backward
+    (tcgen05 3xTF32; the x^T contraction is split-K over the rows, deterministic)."""
+    x, kernel, g = as_f32(x, "x"), as_f32(kernel, "kernel"), as_f32(grad_out, "grad_out")
+    gx = torch.empty_like(x) if need_x else None
+    gk = torch.empty_like(kernel) if need_kernel else None
+    with torch.cuda.device(x.device):
+        check(load_library().rgnn_dense_backward(x.data_ptr(), x.shape[0], x.shape[1], kernel.data_ptr(), kernel.shape[1],
+                                                 g.data_ptr(), gx.data_ptr() if need_x else None,
+                                                 gk.data_ptr() if need_kernel else None, current_stream_ptr(x.device)))
+    return gx, gk
+
+
+class _Linear(torch.autograd.Function):
+    """x @ kernel with both gradients on the engine's GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, kernel):
+        ctx.save_for_backward(x, kernel)
+        return _dense_raw(x, kernel, None, ACT_LINEAR)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, kernel = ctx.saved_tensors
+        gx, gk = dense_backward(x, kernel, grad_out.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return gx, gk
 
 
 def dense(x: torch.Tensor, kernel: torch.Tensor, bias: Optional[torch.Tensor] = None,
           activation: Optional[str] = None) -> torch.Tensor:
     """act(x @ kernel + bias): tf.keras.layers.Dense with the Keras [in, out] kernel,
-    fp32-accurate on the tensor cores (tcgen05 3xTF32)."""
+    fp32-accurate on the tensor cores (tcgen05 3xTF32).  Under autograd the contraction and both of its
+    gradients run on the engine (bias / activation are then applied by torch so that autograd can chain them)."""
     x, kernel = as_f32(x, "x"), as_f32(kernel, "kernel")
     if x.dim() != 2 or kernel.dim() != 2 or x.shape[1] != kernel.shape[0]:
         raise RgnnError(RGNN_E_INVALID, "dense: shapes %s x %s do not contract" % (tuple(x.shape), tuple(kernel.shape)))
     b = as_f32(bias, "bias") if bias is not None else None
-    out = torch.empty((x.shape[0], kernel.shape[1]), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        check(load_library().rgnn_dense_forward(x.data_ptr(), x.shape[0], x.shape[1], kernel.data_ptr(), kernel.shape[1],
-                                                b.data_ptr() if b is not None else None, get_activation(activation),
-                                                out.data_ptr(), current_stream_ptr(x.device)))
-    return out
+    act_code = get_activation(activation)
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or kernel.requires_grad or (b is not None and b.requires_grad))
+    if not needs_grad:
+        return _dense_raw(x, kernel, b, act_code)
+    if x.shape[1] % 4 or kernel.shape[1] % 4:
+        raise RgnnError(RGNN_E_INVALID, "dense: gradients need input / output widths that are multiples of 4")
+    y = _Linear.apply(x, kernel)
+    if b is not None:
+        y = y + b
+    return _TORCH_ACT[act_code](y)
 
 
 def segment_aggregate(plan: GraphPlan, data: torch.Tensor, aggregation: str = "sum") -> torch.Tensor:

@@ -22,11 +22,26 @@ import torch
 
 from .engine import GraphPlan
 from .gnns import sparse_rgcn_layer
+from .ops import dense as engine_dense
 from .weights import glorot_uniform
 
 _ACT = {"tanh": torch.tanh, "relu": torch.relu, "linear": lambda x: x, None: lambda x: x,
         "elu": torch.nn.functional.elu, "gelu": torch.nn.functional.gelu,
         "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.2), "selu": torch.selu}
+
+
+def _matmul(x: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
+    """x @ kernel on the engine's tensor-core GEMM (forward and both gradients).  Widths that are not multiples
+    of 4 (PPI: 50 input features, 121 labels) are zero-padded to the next multiple -- exact, the padding
+    contributes zeros -- so that rows stay 16-byte aligned for the kernels."""
+    k, n = kernel.shape
+    pk, pn = (-k) % 4, (-n) % 4
+    if pk:
+        x = torch.nn.functional.pad(x, (0, pk))
+    if pk or pn:
+        kernel = torch.nn.functional.pad(kernel, (0, pn, 0, pk))
+    y = engine_dense(x, kernel)
+    return y[:, :n] if pn else y
 
 
 def rgcn_ppi_default_params() -> Dict:
@@ -77,7 +92,7 @@ class RGCNPPIModel(torch.nn.Module):
     def node_representations(self, features: torch.Tensor, plan: GraphPlan, num_incoming: torch.Tensor) -> torch.Tensor:
         p = self.params
         act = _ACT[p["graph_model_activation_function"].lower() if p["graph_model_activation_function"] else None]
-        cur = features if self.projection is None else act(features @ self.projection)
+        cur = features if self.projection is None else act(_matmul(features, self.projection))
         last_residual = torch.zeros_like(cur)
         keep = p["graph_layer_input_dropout_keep_prob"]
         for l in range(p["graph_num_layers"]):
@@ -96,20 +111,19 @@ class RGCNPPIModel(torch.nn.Module):
             if p["graph_inter_layer_norm"]:                                                         # :192-193 (eps 1e-12)
                 cur = torch.nn.functional.layer_norm(cur, (p["hidden_size"],), self.inter_ln["g%d" % l], self.inter_ln["b%d" % l], 1e-12)
             if str(l) in self.inter_dense:                                                          # :194-200
-                cur = act(cur @ self.inter_dense[str(l)])
+                cur = act(_matmul(cur, self.inter_dense[str(l)]))
         return cur
 
     def forward(self, features, plan, num_incoming):
-        return self.node_representations(features, plan, num_incoming) @ self.out_kernel + self.out_bias
+        return _matmul(self.node_representations(features, plan, num_incoming), self.out_kernel) + self.out_bias
 
     def task_metrics(self, logits: torch.Tensor, labels: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """tasks/ppi_task.py:181-195."""
+        """tasks/ppi_task.py:181-195.  round(sigmoid(x)) == 1 exactly when x > 0 (round-half-even sends 0.5 to 0),
+        so the predictions are taken from the sign of the logits and the three counts come from one reduction."""
         total = torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="sum")
-        pred = torch.round(torch.sigmoid(logits)).to(torch.int32)
-        lab = labels.to(torch.int32)
-        tp = torch.count_nonzero(pred * lab).double()
-        fp = torch.count_nonzero(pred * (lab - 1)).double()
-        fn = torch.count_nonzero((pred - 1) * lab).double()
+        pred, lab = logits > 0, labels > 0.5
+        counts = torch.stack([pred & lab, pred & ~lab, ~pred & lab]).sum(dim=(1, 2)).double()   # tp, fp, fn
+        tp, fp, fn = counts[0], counts[1], counts[2]
         precision, recall = tp / (tp + fp), tp / (tp + fn)
         return {"loss": total / logits.shape[0], "total_loss": total,
                 "f1_score": (2 * precision * recall / (precision + recall)).float()}
@@ -125,17 +139,32 @@ class RGCNPPIModel(torch.nn.Module):
             return torch.optim.Adam(self.parameters(), lr=p["learning_rate"], eps=1e-8)
         raise Exception('Unknown optimizer "%s".' % p["optimizer"])
 
-    def train_step(self, optimizer, features, plan, num_incoming, labels) -> Dict[str, float]:
-        """One step of __make_train_step: gradients of the per-node loss, per-tensor clip_by_norm, apply."""
+    def clip_gradients_(self) -> None:
+        """tf.clip_by_norm per tensor (:255-258): g * clip / max(||g||, clip) -- evaluated on the device, no host sync."""
+        grads = [q.grad for q in self.parameters() if q.grad is not None]
+        if not grads:
+            return
+        clip = float(self.params["clamp_gradient_norm"])
+        scales = torch._foreach_norm(grads)
+        torch._foreach_clamp_min_(scales, clip)
+        torch._foreach_reciprocal_(scales)
+        torch._foreach_mul_(scales, clip)
+        torch._foreach_mul_(grads, scales)
+
+    def train_step_async(self, optimizer, features, plan, num_incoming, labels) -> Dict[str, torch.Tensor]:
+        """One step of __make_train_step: gradients of the per-node loss, per-tensor clip_by_norm, apply.  Nothing in
+        here waits for the device; the metrics come back as device tensors."""
         self.train()
         optimizer.zero_grad(set_to_none=True)
         m = self.task_metrics(self(features, plan, num_incoming), labels)
         m["loss"].backward()
-        clip = self.params["clamp_gradient_norm"]
-        for q in self.parameters():
-            if q.grad is not None:                                       # tf.clip_by_norm per tensor (:255-258)
-                n = q.grad.norm()
-                if n > clip:
-                    q.grad.mul_(clip / n)
+        self.clip_gradients_()
         optimizer.step()
-        return {k: float(v.detach()) for k, v in m.items()}
+        return {k: v.detach() for k, v in m.items()}
+
+    def train_step(self, optimizer, features, plan, num_incoming, labels) -> Dict[str, float]:
+        """train_step_async + one device->host read of the three metrics."""
+        m = self.train_step_async(optimizer, features, plan, num_incoming, labels)
+        keys = list(m)
+        vals = torch.stack([m[k].float() for k in keys]).tolist()
+        return dict(zip(keys, vals))
