@@ -86,6 +86,54 @@ class RGCNPPIModel(torch.nn.Module):
         L = self.num_edge_types
         return {"edge_weights": [self.edge_weights[l * L + t] for t in range(L)]}
 
+    # ---- reference snapshots (models/sparse_graph_model.py:91-126) ----
+    def reference_variable_names(self) -> Dict[str, str]:
+        from .checkpoint import rgcn_ppi_reference_names
+        names = rgcn_ppi_reference_names(self.params["graph_num_layers"], self.num_edge_types, self.projection is not None,
+                                         [int(k) for k in self.inter_dense])
+        for k in self.inter_ln:                                     # "g<l>" / "b<l>"
+            names["inter_ln." + k] = "gnn_layer_%d/LayerNorm/%s:0" % (int(k[1:]), "gamma" if k[0] == "g" else "beta")
+        return names
+
+    def to_reference_weights(self) -> Dict[str, np.ndarray]:
+        """{tf variable name: array} as Sparse_Graph_Model.save_model stores it."""
+        names = self.reference_variable_names()
+        return {names[n]: p.detach().cpu().numpy() for n, p in self.named_parameters()}
+
+    def load_reference_weights(self, weights: Dict[str, np.ndarray]) -> List[str]:
+        """Assign a reference snapshot's ``weights`` dictionary by variable name (load_weights, :110-126).
+        Returns the names that were not used; raises if a parameter of this model has no saved value or a
+        different shape (the reference would re-initialise it silently -- here that is an error)."""
+        from .checkpoint import scaffold_variables, sort_variables, split_layer_norms
+        srt = sort_variables(weights)
+        H, L = self.params["hidden_size"], self.num_edge_types
+        outside = scaffold_variables(srt["outside"], self.feature_size, H)
+        found: Dict[str, np.ndarray] = {}
+        if self.projection is not None and "projection" in outside:
+            found["projection"] = outside["projection"]
+        for idx, layer in zip(srt["layer_indices"], srt["layers"]):
+            layer = split_layer_norms(layer, 0)                     # RGCN itself has no LayerNorm
+            for t, w in enumerate(layer.get("edge_weights", [])):
+                found["edge_weights.%d" % (idx * L + t)] = w
+            if "inter_dense" in layer:
+                found["inter_dense.%d" % idx] = layer["inter_dense"]
+            if "inter_ln_gamma" in layer:
+                found["inter_ln.g%d" % idx], found["inter_ln.b%d" % idx] = layer["inter_ln_gamma"], layer["inter_ln_beta"]
+        heads = [h for h in outside["head"] if "bias" in h]
+        if heads:
+            found["out_kernel"], found["out_bias"] = heads[-1]["kernel"], heads[-1]["bias"]
+        used = set()
+        with torch.no_grad():
+            for n, p in self.named_parameters():
+                if n not in found:
+                    raise KeyError("reference snapshot has no value for %s" % n)
+                v = np.asarray(found[n], dtype=np.float32)
+                if tuple(v.shape) != tuple(p.shape):
+                    raise ValueError("%s: snapshot shape %s != model shape %s" % (n, v.shape, tuple(p.shape)))
+                p.copy_(torch.as_tensor(v))
+                used.add(n)
+        return list(srt["unused"]) + sorted(outside["other"])
+
     def num_parameters(self) -> int:
         return sum(p.numel() for p in self.parameters())
 
