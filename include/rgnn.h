@@ -202,6 +202,15 @@ RGNN_API int rgnn_rgin_forward(const rgnn_plan_t* plan, const float* node_embedd
  * to [V, d] with the plan's segments -- the tf.unsorted_segment_<agg> call of rgcn.py:110. */
 RGNN_API int rgnn_segment_aggregate(const rgnn_plan_t* plan, const float* data, int32_t d, int aggregation,
                            float* out, void* stream);
+/* The edge stage on per-node transformed states: out[v,:] = agg over the incoming edges (u,v) of every type l of
+ * s * table[u,l,:], table [V, L, d] row-major, s = 1/(num_incoming[l,v] + 1e-7) or 1 when num_incoming is NULL
+ * (gnns/rgcn.py:84-112 and ggnn.py:76-90 with the per-type Dense applied per node first).  The backward gives
+ * d_table[u,l,:] = sum over the outgoing edges (u,v) of type l of s * grad_out[v,:] / div(v) for sum / mean / sqrt_n
+ * (RGNN_E_UNSUPPORTED for max); the reverse index is built inside the plan on first use. */
+RGNN_API int rgnn_edge_aggregate_forward(const rgnn_plan_t* plan, const float* table, int32_t d, const float* num_incoming,
+                                int aggregation, float* out, void* stream);
+RGNN_API int rgnn_edge_aggregate_backward(const rgnn_plan_t* plan, const float* grad_out, int32_t d,
+                                 const float* num_incoming, int aggregation, float* d_table, void* stream);
 /* C[M,N] = act(A[M,K] . B[K,N] + bias) on the tensor cores with 3xTF32 split accumulation
  * (fp32-accurate); the node-level Dense of every layer (A.1). bias may be NULL. */
 RGNN_API int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const float* b, int32_t n,

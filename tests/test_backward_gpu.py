@@ -5,7 +5,7 @@ import pytest
 
 from oracle import ref_grads as RG
 from oracle import ref_layers as R
-from tf_gnn_samples_b200 import GraphPlan, RgnnError, batching, sparse_rgcn_layer, weights as W
+from tf_gnn_samples_b200 import GraphPlan, batching, sparse_rgcn_layer, weights as W
 
 from helpers import assert_parity, node_states, tiny_graph
 
@@ -62,15 +62,19 @@ def test_rgcn_grads_ppi_shaped_two_timesteps(cuda_device):
         assert_parity(d_ws[l], dw1[l] + dw2[l], "d_W[%d] two timesteps (shared kernels)" % l)
 
 
-def test_rgcn_grad_limits(cuda_device):
+def test_rgcn_max_aggregation_under_autograd(cuda_device):
+    """max aggregation is outside the fused backward kernels: it takes the composed path (gnns/_train.py) and still
+    returns gradients (compared with the oracle in test_train_layers_gpu.py)."""
     import torch
     adj, indeg = tiny_graph()
     h = torch.as_tensor(node_states(37, 64)).to(cuda_device).requires_grad_(True)
     w = {"edge_weights": [torch.as_tensor(k).to(cuda_device) for k in W.rgcn_weights(4, 64, 64)["edge_weights"]]}
-    with pytest.raises(RgnnError):
-        sparse_rgcn_layer(h, adj, indeg, 64, message_aggregation_function="max", weights=w)
-    with torch.no_grad():   # inference with max aggregation still works
-        sparse_rgcn_layer(h, adj, indeg, 64, message_aggregation_function="max", weights=w)
+    out = sparse_rgcn_layer(h, adj, indeg, 64, message_aggregation_function="max", weights=w)
+    out.sum().backward()
+    assert h.grad is not None and torch.isfinite(h.grad).all()
+    with torch.no_grad():   # inference with max aggregation: the fused kernel
+        ref = sparse_rgcn_layer(h, adj, indeg, 64, message_aggregation_function="max", weights=w)
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5)
 
 
 def test_rgcn_grads_with_heavy_segments(cuda_device):

@@ -722,6 +722,57 @@ extern "C" int rgnn_segment_aggregate(const rgnn_plan_t* plan, const float* data
   return launch_seg_reduce(s, stream);
 }
 
+// The edge stage on per-node transformed states (rgcn.py:84-112, ggnn.py:76-90 after re-association):
+// out[v] = agg_{l, (u,v) in A_l} s_{l,v} * table[u, l, :]
+extern "C" int rgnn_edge_aggregate_forward(const rgnn_plan_t* plan, const float* table, int32_t d, const float* num_incoming,
+                                           int aggregation, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_REQUIRE(plan != nullptr && table != nullptr && out != nullptr, "edge_aggregate: NULL argument");
+  RGNN_REQUIRE(d > 0 && (d % 4) == 0 && aligned16(table) && aligned16(out), "edge_aggregate: d must be a positive multiple of 4, rows 16-byte aligned");
+  RGNN_PROPAGATE(check_agg(aggregation, "edge_aggregate"));
+  SegParams s;
+  seg_from_plan(s, plan);
+  s.D = d; s.table = table; s.stride_idx = (long)plan->L * d; s.stride_type = d;
+  s.num_incoming = num_incoming;
+  s.agg = aggregation; s.out = out; s.ld_out = d;
+  return launch_seg_reduce(s, stream);
+}
+
+// d_table[u, l, :] = sum_{(u,v) in A_l} s_{l,v} * grad_out[v, :] / div(v)   (reverse index: segments = (source, type))
+extern "C" int rgnn_edge_aggregate_backward(const rgnn_plan_t* plan_c, const float* grad_out, int32_t d,
+                                            const float* num_incoming, int aggregation, float* d_table, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  rgnn_plan* plan = const_cast<rgnn_plan*>(plan_c);
+  RGNN_REQUIRE(plan != nullptr && grad_out != nullptr && d_table != nullptr, "edge_aggregate_backward: NULL argument");
+  RGNN_REQUIRE(d > 0 && (d % 4) == 0 && aligned16(grad_out) && aligned16(d_table), "edge_aggregate_backward: d must be a positive multiple of 4, rows 16-byte aligned");
+  RGNN_PROPAGATE(check_agg(aggregation, "edge_aggregate_backward"));
+  if (aggregation == RGNN_AGG_MAX) {
+    set_error("edge_aggregate_backward: the gradient of 'max' aggregation is not implemented in this kernel");
+    return RGNN_E_UNSUPPORTED;
+  }
+  RGNN_PROPAGATE(plan_ensure_reverse(plan, stream));
+  const int V = plan->V, L = plan->L;
+  const float* d_agg = grad_out;
+  float* scratch = nullptr;
+  if (aggregation != RGNN_AGG_SUM) {   // mean / sqrt_n: divide by the segment size first
+    RGNN_CHECK_CUDA(cudaMallocAsync(&scratch, sizeof(float) * (size_t)(V > 0 ? V : 1) * d, stream));
+    const int rc = launch_act_backward(grad_out, grad_out, nullptr, V, d, RGNN_ACT_LINEAR, aggregation, plan->seg_off, scratch, stream);
+    if (rc != RGNN_OK) { cudaFreeAsync(scratch, stream); return rc; }
+    d_agg = scratch;
+  }
+  SegParams r;
+  r.V = V * L; r.L = L; r.D = d;
+  r.seg_off = plan->rev_seg_off; r.e_idx = plan->rev_src; r.e_type = plan->rev_type;
+  r.table = d_agg; r.stride_idx = d; r.stride_type = 0;
+  r.num_incoming = num_incoming; r.scale_ld = V; r.scale_by_idx = 1;
+  r.heavy_list = plan->rev_heavy_list; r.heavy_count = plan->err_flag + 2;
+  r.heavy_threshold = RGNN_HEAVY_SEGMENT; r.heavy_known = -1;
+  r.agg = RGNN_AGG_SUM; r.out = d_table; r.ld_out = d;
+  const int rc = launch_seg_reduce(r, stream);
+  if (scratch != nullptr) cudaFreeAsync(scratch, stream);
+  return rc;
+}
+
 extern "C" int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const float* b, int32_t n, const float* bias,
                                   int activation, float* c, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

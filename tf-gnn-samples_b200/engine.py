@@ -60,6 +60,8 @@ SIGNATURES = {
     "rgnn_rgin_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, _PTR, _PTR, c_int, _PTR, _PTR,
                                   c_int, c_int, c_int, c_int, _PTR, _PTR, c_size_t, _PTR]),
     "rgnn_segment_aggregate": (c_int, [_PTR, _PTR, c_int32, c_int, _PTR, _PTR]),
+    "rgnn_edge_aggregate_forward": (c_int, [_PTR, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
+    "rgnn_edge_aggregate_backward": (c_int, [_PTR, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
     "rgnn_dense_forward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
     "rgnn_dense_backward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, _PTR, _PTR, _PTR]),
     "rgnn_layer_norm": (c_int, [_PTR, c_int32, c_int32, _PTR, _PTR, _PTR, _PTR]),
@@ -244,6 +246,62 @@ class GraphPlan:
         if self._handle is None:
             raise RgnnError(RGNN_E_INVALID, "GraphPlan used after close()")
         return self._handle
+
+    # ---- index views used by the differentiable building blocks (ops.py); built lazily, cached ----
+    def _cached(self, key, make):
+        cache = self.__dict__.setdefault("_derived", {})
+        if key not in cache:
+            cache[key] = make()
+        return cache[key]
+
+    @property
+    def message_sources(self) -> torch.Tensor:
+        """int64 [M]: source of every message, type-major concatenation order (gnns/rgcn.py:85,108)."""
+        return self._cached("src", lambda: torch.cat([a[:, 0] for a in self.adjacency_lists]).long())
+
+    @property
+    def message_targets(self) -> torch.Tensor:
+        """int64 [M]: target of every message (gnns/rgcn.py:78)."""
+        return self._cached("tgt", lambda: torch.cat([a[:, 1] for a in self.adjacency_lists]).long())
+
+    @property
+    def message_types(self) -> torch.Tensor:
+        return self._cached("typ", lambda: torch.cat([torch.full((a.shape[0],), l, dtype=torch.long, device=self.device)
+                                                      for l, a in enumerate(self.adjacency_lists)]))
+
+    @property
+    def type_offsets(self) -> List[int]:
+        off = [0]
+        for a in self.adjacency_lists:
+            off.append(off[-1] + int(a.shape[0]))
+        return off
+
+    @property
+    def in_degree(self) -> torch.Tensor:
+        """float32 [V]: incoming messages per node over all types (the segment sizes of tf.unsorted_segment_mean)."""
+        return self._cached("indeg", lambda: torch.bincount(self.message_targets, minlength=self.num_nodes).float())
+
+    def regrouped(self, by: str) -> "GraphPlan":
+        """A plan over the SAME messages (same type-major row order of per-edge matrices) whose segments are
+        'source': the source node; 'source_type': (source, type) -> segment u*L + l; 'target_type': (target, type).
+        Segment-summing per-edge gradients with these plans is the (deterministic) backward of the gathers."""
+        L = self.num_edge_types
+
+        def make():
+            lists = []
+            for l, a in enumerate(self.adjacency_lists):
+                src, tgt = a[:, 0], a[:, 1]
+                if by == "source":
+                    lists.append(torch.stack([tgt, src], dim=1))
+                elif by == "source_type":
+                    lists.append(torch.stack([tgt, src * L + l], dim=1))
+                elif by == "target_type":
+                    lists.append(torch.stack([src, tgt * L + l], dim=1))
+                else:
+                    raise RgnnError(RGNN_E_INVALID, "unknown regrouping '%s'" % by)
+            n = self.num_nodes if by == "source" else self.num_nodes * L
+            return GraphPlan(lists, n, device=self.device, validate=False)
+        return self._cached("plan_" + by, make)
 
     def check(self):
         """Synchronise the creation stream and raise if the index-range check failed (deferred validation)."""

@@ -7,6 +7,7 @@ from ..utils import LAYER_GGNN, CELL_GRU, get_aggregation_function, get_gated_un
 from ..engine import note_weights
 from ._common import (RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, load_library, prepare, ptr_table,
                       weight_list, workspace)
+from . import _train
 
 
 def sparse_ggnn_layer(node_embeddings: torch.Tensor,
@@ -39,6 +40,9 @@ def sparse_ggnn_layer(node_embeddings: torch.Tensor,
         raise RgnnError(RGNN_E_INVALID, "sparse_ggnn_layer: cell weights must be [%d,%d], [%d,%d], [%d]; got %s %s %s"
                         % (d_out, gates * d_out, d_out, gates * d_out, gates * d_out,
                            tuple(kernel.shape), tuple(rec.shape), tuple(bias.shape)))
+    if _train.requires_grad(h, ws, kernel, rec, bias):               # training: differentiable composition (gnns/_train.py)
+        return _train.ggnn(h, plan, ws, {"kernel": kernel, "recurrent_kernel": rec, "bias": bias},
+                           "gru" if cell_kind == CELL_GRU else "rnn", act, message_aggregation_function, num_timesteps)
     note_weights([kernel, rec, bias])
     lib = load_library()
     out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)

@@ -6,6 +6,7 @@ import torch
 from ..utils import LAYER_EDGE_MLP, get_activation, get_aggregation_function
 from ._common import (RgnnError, RGNN_E_INVALID, check, current_stream_ptr, int32_array, layer_norm_params,
                       load_library, mlp_tables, num_incoming_tensor, prepare, ptr_table, workspace)
+from . import _train
 
 
 def sparse_gnn_edge_mlp_layer(node_embeddings: torch.Tensor,
@@ -38,6 +39,10 @@ def sparse_gnn_edge_mlp_layer(node_embeddings: torch.Tensor,
                         "type, got %d" % (num_edge_hidden_layers, num_edge_hidden_layers + 1, nl))
     cnt = num_incoming_tensor(type_to_num_incoming_edges, plan, normalize_by_num_incoming)
     g, b = layer_norm_params(weights, int(num_timesteps), d_out, h.device)
+    if _train.requires_grad(h, flat, g, b):                           # training: differentiable composition (gnns/_train.py)
+        per_type = [flat[l * nl:(l + 1) * nl] for l in range(L)]
+        return _train.edge_mlp(h, plan, cnt, per_type, (g, b), act, message_aggregation_function,
+                               bool(use_target_state_as_input), num_timesteps)
     lib = load_library()
     out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
     with torch.cuda.device(h.device):

@@ -6,6 +6,7 @@ import torch
 from ..utils import LAYER_FILM, get_activation, get_aggregation_function
 from ._common import (check, current_stream_ptr, layer_norm_params, load_library, num_incoming_tensor, prepare,
                       ptr_table, weight_list, workspace)
+from . import _train
 
 
 def sparse_gnn_film_layer(node_embeddings: torch.Tensor,
@@ -31,6 +32,8 @@ def sparse_gnn_film_layer(node_embeddings: torch.Tensor,
     fw = weight_list(weights, "film_weights", L, (d_in, 2 * d_out), "sparse_gnn_film_layer")
     cnt = num_incoming_tensor(type_to_num_incoming_edges, plan, normalize_by_num_incoming)
     g, b = layer_norm_params(weights, int(num_timesteps), d_out, h.device)
+    if _train.requires_grad(h, ws, fw, g, b):                         # training: differentiable composition (gnns/_train.py)
+        return _train.film(h, plan, cnt, ws, fw, (g, b), act, message_aggregation_function, num_timesteps)
     lib = load_library()
     out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
     with torch.cuda.device(h.device):

@@ -5,6 +5,7 @@ import torch
 
 from ..utils import LAYER_RGAT, get_activation
 from ._common import (check, current_stream_ptr, load_library, prepare, ptr_table, weight_list, workspace)
+from . import _train
 
 
 def sparse_rgat_layer(node_embeddings: torch.Tensor,
@@ -27,6 +28,10 @@ def sparse_rgat_layer(node_embeddings: torch.Tensor,
     L = plan.num_edge_types
     ws = weight_list(weights, "edge_weights", L, (d_in, d_out), "sparse_rgat_layer")
     att = weight_list(weights, "attention", L, (2 * d_out,), "sparse_rgat_layer")
+    if d_out % int(num_heads):
+        raise RgnnError(RGNN_E_INVALID, "sparse_rgat_layer: state_dim %d is not divisible by num_heads %d" % (d_out, num_heads))
+    if _train.requires_grad(h, ws, att):                              # training: differentiable composition (gnns/_train.py)
+        return _train.rgat(h, plan, ws, att, int(num_heads), act, num_timesteps)
     lib = load_library()
     out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
     with torch.cuda.device(h.device):

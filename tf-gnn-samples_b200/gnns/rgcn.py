@@ -3,10 +3,10 @@ from typing import Dict, List, Optional
 
 import torch
 
-from ..engine import RgnnError, RGNN_E_UNSUPPORTED
 from ..utils import AGG_MAX, LAYER_RGCN, LAYER_RGCN_BACKWARD, get_activation, get_aggregation_function
 from ._common import (check, current_stream_ptr, load_library, num_incoming_tensor, prepare, ptr_table, weight_list,
                       workspace)
+from . import _train
 
 
 def _forward_raw(h, plan, cnt, ws, d_in, d_out, act, agg, normalize, both, num_timesteps):
@@ -90,8 +90,8 @@ def sparse_rgcn_layer(node_embeddings: torch.Tensor,
                             use_both_source_and_target, num_timesteps)
     # training path: one differentiable step per timestep (autograd chains them)
     if use_both_source_and_target or agg == AGG_MAX:
-        raise RgnnError(RGNN_E_UNSUPPORTED, "sparse_rgcn_layer: gradients are implemented for source-only messages and "
-                        "sum / mean / sqrt_n aggregation (use torch.no_grad() for inference with other settings)")
+        # settings outside the fused backward kernels: differentiable composition of the engine's building blocks
+        return _train.rgcn(h, plan, cnt, ws, act, message_aggregation_function, bool(use_both_source_and_target), num_timesteps)
     cur = h
     for _ in range(int(num_timesteps)):
         cur = _RGCNStep.apply(cur, plan, cnt, act, agg, bool(normalize_by_num_incoming), *ws)

@@ -6,6 +6,7 @@ import torch
 from ..utils import LAYER_RGIN, get_activation, get_aggregation_function
 from ._common import (RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, int32_array, layer_norm_params,
                       load_library, mlp_tables, prepare, ptr_table, workspace)
+from . import _train
 
 
 def sparse_rgin_layer(node_embeddings: torch.Tensor,
@@ -49,6 +50,11 @@ def sparse_rgin_layer(node_embeddings: torch.Tensor,
         adims = [int(ks[0].shape[0])] + [int(k.shape[1]) for k in ks]
         aggr_keep, aggr_ptrs, aggr_dims, n_aggr_hidden = ks, ptr_table(ks), int32_array(adims), int(num_aggr_MLP_hidden_layers)
     g, b = layer_norm_params(weights, int(num_timesteps), d_out, h.device)
+    if _train.requires_grad(h, weights.get("edge_mlps") if edge_ptrs is not None else None,
+                            weights.get("aggr_mlp") if aggr_ptrs is not None else None, g, b):   # training (gnns/_train.py)
+        per_type = [edge_keep[l * nl_edge:(l + 1) * nl_edge] for l in range(L)] if edge_ptrs is not None else None
+        return _train.rgin(h, plan, per_type, aggr_keep if aggr_ptrs is not None else None, (g, b), act,
+                           message_aggregation_function, bool(use_target_state_as_input), num_timesteps)
     lib = load_library()
     out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
     with torch.cuda.device(h.device):
