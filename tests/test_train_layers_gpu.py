@@ -46,7 +46,9 @@ def compare(engine_fn, oracle_fn, h, w, proj_seed=0, tol=TOL):
         if f64[k].grad is None:
             assert fd[k].grad is None or float(fd[k].grad.abs().max()) == 0.0, k
             continue
-        assert fd[k].grad is not None, "no gradient reached %s" % k
+        if fd[k].grad is None:                                   # e.g. the kernel of an edge type without edges: autograd never sees it
+            assert float(f64[k].grad.abs().max()) == 0.0, "no gradient reached %s" % k
+            continue
         errs["d_" + k] = rel(fd[k].grad.cpu().numpy(), f64[k].grad.numpy())
     print({k: "%.1e" % v for k, v in errs.items()})
     bad = {k: v for k, v in errs.items() if not v <= tol}
@@ -78,8 +80,8 @@ def test_building_blocks(cuda_device):
     M = plan.num_edges
     data = rng.standard_normal((M, D)).astype(np.float32)
     data[5] = data[4]                                        # a tie for the max gradient (rows 4, 5 share a target? not necessarily)
-    src = np.concatenate([a[:, 0] for a in adj]); tgt = np.concatenate([a[:, 1] for a in adj])
-    typ = np.concatenate([np.full(a.shape[0], l) for l, a in enumerate(adj)])
+    src = np.concatenate([a[:, 0] for a in adj]).astype(np.int64); tgt = np.concatenate([a[:, 1] for a in adj]).astype(np.int64)
+    typ = np.concatenate([np.full(a.shape[0], l, dtype=np.int64) for l, a in enumerate(adj)])
     cnt64 = torch.as_tensor(indeg, dtype=torch.float64)
     for agg in ["sum", "mean", "sqrt_n", "max"]:
         proj = rng.standard_normal((V, D))
