@@ -115,3 +115,54 @@ def test_weight_shapes():
     assert [k.shape for k in e["edge_mlps"][0]] == [(32, 24), (24, 24), (24, 24)]
     r = W.rgin_weights(2, 16, 24, num_edge_MLP_hidden_layers=None, num_aggr_MLP_hidden_layers=1, use_target_state_as_input=True)
     assert "edge_mlps" not in r and [k.shape for k in r["aggr_mlp"]] == [(32, 24), (24, 24)]
+
+
+def _qm9_subset():
+    import os
+    from tf_gnn_samples_b200 import batching
+    return batching.load_qm9_jsonl(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qm9_valid_subset.json.gz"))
+
+
+def test_qm9_records_to_batch_follows_the_reference_loader():
+    """tasks/qm9_task.py:85-147,200-261 on 200 real QM9 validation records (tests/golden/make_qm9_subset.py)."""
+    from tf_gnn_samples_b200 import batching
+    recs = _qm9_subset()
+    assert len(recs) == 200 and len(recs[0]["node_features"][0]) == 15 and len(recs[0]["targets"]) == 13
+    raw_bonds = sum(len(r["graph"]) for r in recs)
+    V = sum(len(r["node_features"]) for r in recs)
+    b, graph_nodes_list, targets = batching.qm9_batch(recs)                       # defaults: self loops, tied directions
+    assert len(b.adjacency_lists) == 5 and b.num_nodes == V and b.num_graphs == 200
+    assert b.num_edges == 2 * raw_bonds + V                                      # both directions in the bond's type + one loop per node
+    assert b.adjacency_lists[0].shape[0] == V and np.all(b.adjacency_lists[0][:, 0] == b.adjacency_lists[0][:, 1])
+    assert np.all(b.type_to_num_incoming_edges[0] == 1)
+    for l, a in enumerate(b.adjacency_lists):                                    # in-degrees are the bincount of the targets
+        assert np.array_equal(b.type_to_num_incoming_edges[l], np.bincount(a[:, 1], minlength=V)), l
+    first = batching.qm9_graph_to_sample(recs[0], 5)
+    for a in first.adjacency_lists:                                              # sorted by (src, dst) (:135)
+        assert [tuple(x) for x in a] == sorted(tuple(x) for x in a)
+    assert graph_nodes_list.shape == (V,) and graph_nodes_list[0] == 0 and graph_nodes_list[-1] == 199
+    assert targets.shape == (1, 200) and np.isclose(targets[0, 0], recs[0]["targets"][0][0])
+    b4, _, _ = batching.qm9_batch(recs, add_self_loop_edges=False)                # BASELINE's "4 edge types"
+    assert len(b4.adjacency_lists) == 4 and b4.num_edges == 2 * raw_bonds
+    bu, _, _ = batching.qm9_batch(recs[:20], tie_fwd_bkwd_edges=False)            # untied: reversed lists as extra types
+    assert len(bu.adjacency_lists) == 10
+    for t in range(5):
+        assert np.array_equal(np.sort(bu.adjacency_lists[5 + t][:, ::-1], axis=0), np.sort(bu.adjacency_lists[t], axis=0))
+    small, _, _ = batching.qm9_batch(recs, max_nodes_per_batch=100)               # the packing loop stops before the limit
+    assert small.num_nodes < 100 and small.num_graphs < 200
+
+
+def test_qm9_full_validation_set_counts_when_the_reference_data_is_present():
+    """10,000 graphs, V = 180,560, M = 373,466 (L=4) / 554,026 (L=5).  Only runs where
+    /root/reference exists (the build container)."""
+    import os
+    import pytest
+    from tf_gnn_samples_b200 import batching
+    path = "/root/reference/data/qm9/valid.jsonl.gz"
+    if not os.path.exists(path):
+        pytest.skip("reference data not present")
+    recs = batching.load_qm9_jsonl(path)
+    b5, _, _ = batching.qm9_batch(recs)
+    b4, _, _ = batching.qm9_batch(recs, add_self_loop_edges=False)
+    assert (b5.num_graphs, b5.num_nodes, b5.num_edges, len(b5.adjacency_lists)) == (10000, 180560, 554026, 5)
+    assert (b4.num_nodes, b4.num_edges, len(b4.adjacency_lists)) == (180560, 373466, 4)

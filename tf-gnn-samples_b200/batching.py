@@ -91,6 +91,74 @@ def make_qm9_like_graphs(num_graphs: int, seed: int = 0, add_self_loop_edges: bo
     return [make_qm9_like_graph(rng, add_self_loop_edges=add_self_loop_edges) for _ in range(num_graphs)]
 
 
+# ---- real QM9 records (data/qm9/*.jsonl.gz of the reference; tasks/qm9_task.py:85-147) ----
+def qm9_num_edge_types(raw_graphs: Sequence[Dict], add_self_loop_edges: bool = True, tie_fwd_bkwd_edges: bool = True) -> int:
+    """tasks/qm9_task.py:89-96: max bond type (+1 for the self-loop type 0), doubled when directions are untied."""
+    num_fwd = max(max(e[1] for e in g["graph"]) for g in raw_graphs if len(g["graph"]))
+    if add_self_loop_edges:
+        num_fwd += 1
+    return num_fwd * (1 if tie_fwd_bkwd_edges else 2)
+
+
+def qm9_graph_to_sample(raw: Dict, num_edge_types: int, add_self_loop_edges: bool = True,
+                        tie_fwd_bkwd_edges: bool = True) -> GraphSample:
+    """One record {"graph": [(src, bond, dst)...], "node_features": [[15 floats]...]} -> per-type adjacency lists and
+    in-degrees exactly as __graph_to_adjacency_lists builds them (tasks/qm9_task.py:114-147): bond types start at 1
+    (0 is the self-loop type when enabled, else types are shifted down by one); tied directions put (dst, src) in the
+    same type; each list is sorted by (src, dst); untied directions append the reversed lists as extra types."""
+    num_nodes = len(raw["node_features"])
+    lists: List[List] = [[] for _ in range(num_edge_types)]
+    indeg = np.zeros((num_edge_types, num_nodes), dtype=np.float64)
+    for src, e, dst in raw["graph"]:
+        t = e if add_self_loop_edges else e - 1
+        lists[t].append((src, dst))
+        indeg[t, dst] += 1
+        if tie_fwd_bkwd_edges:
+            lists[t].append((dst, src))
+            indeg[t, src] += 1
+    if add_self_loop_edges:
+        for v in range(num_nodes):
+            indeg[0, v] = 1
+            lists[0].append((v, v))
+    adj = [np.array(sorted(l), dtype=np.int32).reshape(-1, 2) for l in lists]
+    if not tie_fwd_bkwd_edges:
+        half = num_edge_types // 2
+        adj = adj[:half]
+        for t in range(half):
+            adj.append(np.array(sorted((y, x) for (x, y) in adj[t]), dtype=np.int32).reshape(-1, 2))
+            for (x, y) in adj[t]:
+                indeg[half + t][y] += 1      # as the reference counts it (:143-144): at the forward edge's target y,
+                                             # although the reversed edge (y, x) arrives at x -- kept for identical feeds
+    return GraphSample(adj, indeg.astype(np.float32), np.asarray(raw["node_features"], dtype=np.float32))
+
+
+def load_qm9_jsonl(path: str, limit: Optional[int] = None) -> List[Dict]:
+    """Read records of a reference data/qm9/*.jsonl.gz file (dpu_utils RichPath.read_by_file_suffix in the reference)."""
+    import gzip
+    import json
+    out = []
+    with gzip.open(path, "rt") as f:
+        for line in f:
+            out.append(json.loads(line))
+            if limit is not None and len(out) >= limit:
+                break
+    return out
+
+
+def qm9_batch(raw_graphs: Sequence[Dict], add_self_loop_edges: bool = True, tie_fwd_bkwd_edges: bool = True,
+              task_ids: Sequence[int] = (0,), max_nodes_per_batch: Optional[int] = None):
+    """Records -> (Batch, graph_nodes_list int32 [V], target_values float32 [len(task_ids), G]): the feed_dict of
+    tasks/qm9_task.py:200-261 for one minibatch."""
+    L = qm9_num_edge_types(raw_graphs, add_self_loop_edges, tie_fwd_bkwd_edges)
+    samples = [qm9_graph_to_sample(g, L, add_self_loop_edges, tie_fwd_bkwd_edges) for g in raw_graphs]
+    batch = pack_batch(samples, max_nodes_per_batch)
+    G = batch.num_graphs
+    sizes = np.diff(batch.graph_node_offsets)
+    graph_nodes_list = np.repeat(np.arange(G, dtype=np.int32), sizes)
+    targets = np.array([[raw_graphs[g]["targets"][t][0] for g in range(G)] for t in task_ids], dtype=np.float32)
+    return batch, graph_nodes_list, targets
+
+
 def make_typed_random_graph(num_nodes: int, num_edges: int, type_fractions: Sequence[float], feature_dim: int,
                             seed: int = 0) -> GraphSample:
     """Uniform random multigraph with the edges split over L types in the given proportions

@@ -216,3 +216,253 @@ class RGCNPPIModel(torch.nn.Module):
         keys = list(m)
         vals = torch.stack([m[k].float() for k in keys]).tolist()
         return dict(zip(keys, vals))
+
+
+# =====================================================================================================================
+# General scaffold: any of the six layer families under either task head
+# =====================================================================================================================
+_BASE_DEFAULTS = {                                             # Sparse_Graph_Model.default_params (models/sparse_graph_model.py:33-55)
+    "max_nodes_in_batch": 50000, "graph_num_layers": 8, "graph_num_timesteps_per_layer": 1,
+    "graph_layer_input_dropout_keep_prob": 0.8, "graph_dense_between_every_num_gnn_layers": 1,
+    "graph_model_activation_function": "tanh", "graph_residual_connection_every_num_layers": 2,
+    "graph_inter_layer_norm": False, "optimizer": "Adam", "learning_rate": 0.001, "learning_rate_decay": 0.98,
+    "momentum": 0.85, "clamp_gradient_norm": 1.0, "random_seed": 0,
+}
+_MODEL_DEFAULTS = {                                            # <X>_Model.default_params overlays (models/*_model.py)
+    "rgcn": {"hidden_size": 128, "graph_activation_function": "ReLU", "message_aggregation_function": "sum",
+             "graph_layer_input_dropout_keep_prob": 1.0, "graph_dense_between_every_num_gnn_layers": 10000,
+             "graph_residual_connection_every_num_layers": 10000},
+    "ggnn": {"hidden_size": 128, "graph_rnn_cell": "GRU", "graph_activation_function": "tanh",
+             "message_aggregation_function": "sum", "graph_layer_input_dropout_keep_prob": 1.0,
+             "graph_dense_between_every_num_gnn_layers": 10000, "graph_residual_connection_every_num_layers": 10000},
+    "rgat": {"hidden_size": 128, "num_heads": 4, "graph_activation_function": "tanh",
+             "graph_layer_input_dropout_keep_prob": 1.0, "graph_dense_between_every_num_gnn_layers": 10000,
+             "graph_residual_connection_every_num_layers": 10000},
+    "rgin": {"hidden_size": 128, "graph_activation_function": "ReLU", "message_aggregation_function": "sum",
+             "graph_dense_between_every_num_gnn_layers": 10000, "graph_inter_layer_norm": True,
+             "use_target_state_as_input": False, "graph_num_edge_MLP_hidden_layers": 1,
+             "graph_num_aggr_MLP_hidden_layers": None},
+    "gnn-edge-mlp": {"max_nodes_in_batch": 25000, "hidden_size": 128, "graph_activation_function": "gelu",
+                     "message_aggregation_function": "sum", "graph_inter_layer_norm": True,
+                     "use_target_state_as_input": True, "num_edge_hidden_layers": 1},
+    "gnn-film": {"hidden_size": 128, "graph_activation_function": "ReLU", "message_aggregation_function": "sum",
+                 "normalize_messages_by_num_incoming": False},
+}
+_MODEL_ALIASES = {"rgcn_model": "rgcn", "ggnn_model": "ggnn", "rgat_model": "rgat", "rgin_model": "rgin",
+                  "gnn_edge_mlp": "gnn-edge-mlp", "gnn-edge_mlp": "gnn-edge-mlp", "gnn_edge_mlp_model": "gnn-edge-mlp",
+                  "gnn_film": "gnn-film", "gnn_film_model": "gnn-film"}
+_LAYERS_WITH_OWN_LN = ("rgin", "gnn-edge-mlp", "gnn-film")      # one LayerNorm per timestep inside the layer function
+
+
+def model_default_params(model: str) -> Dict:
+    """name_to_model_class(...)[0].default_params() of the reference (utils/model_utils.py:30-55)."""
+    kind = _MODEL_ALIASES.get(model.lower(), model.lower())
+    if kind not in _MODEL_DEFAULTS:
+        raise ValueError("Unknown model type '%s'" % model)
+    return dict(_BASE_DEFAULTS, **_MODEL_DEFAULTS[kind])
+
+
+class SparseGraphModel(torch.nn.Module):
+    """Sparse_Graph_Model with one of the six GNN layer families and a PPI (node classification) or QM9 (graph
+    regression) head.  Inference runs the fused layer kernels; under autograd the layers take their differentiable
+    paths (gnns/_train.py), so ``train_step`` works for every family."""
+
+    def __init__(self, model: str, task: str, num_edge_types: int, feature_size: int, params: Optional[Dict] = None,
+                 num_labels: int = 121, task_ids=(0,), device="cuda"):
+        super().__init__()
+        from . import weights as W
+        self.kind = _MODEL_ALIASES.get(model.lower(), model.lower())
+        self.task = task.lower()
+        if self.task not in ("ppi", "qm9"):
+            raise ValueError("Unknown task type '%s'" % task)
+        self.params = dict(model_default_params(self.kind), **(params or {}))
+        p = self.params
+        H, L, T = p["hidden_size"], num_edge_types, p["graph_num_timesteps_per_layer"]
+        self.num_edge_types, self.feature_size, self.task_ids = L, feature_size, tuple(task_ids)
+        self._device = torch.device(device)
+        rng = np.random.default_rng(p["random_seed"])
+        self._count = 0
+        self.projection = self._param(glorot_uniform(rng, feature_size, H)) if feature_size != H else None
+        self.layers: List[Dict] = []
+        for l in range(p["graph_num_layers"]):
+            seed = p["random_seed"] * 1000 + 17 * l + 1
+            if self.kind == "rgcn":
+                w = W.rgcn_weights(L, H, H, seed)
+            elif self.kind == "ggnn":
+                w = W.ggnn_weights(L, H, seed, cell=p["graph_rnn_cell"])
+            elif self.kind == "rgat":
+                w = W.rgat_weights(L, H, H, seed)
+            elif self.kind == "gnn-film":
+                w = W.film_weights(L, H, H, seed, num_timesteps=T)
+            elif self.kind == "gnn-edge-mlp":
+                w = W.edge_mlp_weights(L, H, H, p["num_edge_hidden_layers"], p["use_target_state_as_input"], seed, num_timesteps=T)
+            else:
+                w = W.rgin_weights(L, H, H, p["graph_num_edge_MLP_hidden_layers"], p["graph_num_aggr_MLP_hidden_layers"],
+                                   p["use_target_state_as_input"], seed, num_timesteps=T)
+            extras = {}
+            if p["graph_inter_layer_norm"]:
+                extras["inter_ln_gamma"], extras["inter_ln_beta"] = np.ones(H, np.float32), np.zeros(H, np.float32)
+            if l % p["graph_dense_between_every_num_gnn_layers"] == 0:
+                extras["inter_dense"] = glorot_uniform(rng, H, H)
+            self.layers.append(self._register("gnn_layer_%d" % l, dict(w, **extras)))
+        if self.task == "ppi":
+            self.head = self._register("head", {"kernel": glorot_uniform(rng, H, num_labels), "bias": np.zeros(num_labels, np.float32)})
+        else:                                                    # tasks/qm9_task.py:162-176: per task a gate on [h | x0] and a transform on h
+            self.head = self._register("head", [{"gate_kernel": glorot_uniform(rng, H + feature_size, 1), "gate_bias": np.zeros(1, np.float32),
+                                                 "kernel": glorot_uniform(rng, H, 1), "bias": np.zeros(1, np.float32)}
+                                                for _ in self.task_ids])
+
+    # ---- parameter plumbing: nested containers of Parameters, registered under flat names ----
+    def _param(self, array, name: Optional[str] = None):
+        q = torch.nn.Parameter(torch.as_tensor(np.ascontiguousarray(array), dtype=torch.float32, device=self._device))
+        self.register_parameter(name or "projection", q)
+        return q
+
+    def _register(self, prefix: str, obj):
+        if isinstance(obj, dict):
+            return {k: self._register("%s__%s" % (prefix, k), v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return [self._register("%s__%d" % (prefix, i), v) for i, v in enumerate(obj)]
+        if obj is None or isinstance(obj, str):
+            return obj
+        return self._param(obj, prefix)
+
+    def num_parameters(self) -> int:
+        return sum(q.numel() for q in self.parameters())
+
+    # ---- models/<x>_model.py: _apply_gnn_layer ----
+    def _apply_gnn_layer(self, cur, plan, cnt, w):
+        from . import gnns as G
+        p, H, T = self.params, self.params["hidden_size"], self.params["graph_num_timesteps_per_layer"]
+        act = p["graph_activation_function"]
+        if self.kind == "rgcn":
+            return G.sparse_rgcn_layer(cur, plan, cnt, H, num_timesteps=T, activation_function=act,
+                                       message_aggregation_function=p["message_aggregation_function"], weights=w)
+        if self.kind == "ggnn":
+            return G.sparse_ggnn_layer(cur, plan, H, num_timesteps=T, gated_unit_type=p["graph_rnn_cell"], activation_function=act,
+                                       message_aggregation_function=p["message_aggregation_function"], weights=w)
+        if self.kind == "rgat":
+            return G.sparse_rgat_layer(cur, plan, H, num_timesteps=T, num_heads=p["num_heads"], activation_function=act, weights=w)
+        if self.kind == "gnn-film":
+            return G.sparse_gnn_film_layer(cur, plan, cnt, H, num_timesteps=T, activation_function=act,
+                                           message_aggregation_function=p["message_aggregation_function"],
+                                           normalize_by_num_incoming=p["normalize_messages_by_num_incoming"], weights=w)
+        if self.kind == "gnn-edge-mlp":
+            return G.sparse_gnn_edge_mlp_layer(cur, plan, cnt, H, num_timesteps=T, activation_function=act,
+                                               message_aggregation_function=p["message_aggregation_function"],
+                                               use_target_state_as_input=p["use_target_state_as_input"],
+                                               num_edge_hidden_layers=p["num_edge_hidden_layers"], weights=w)
+        return G.sparse_rgin_layer(cur, plan, H, num_timesteps=T, activation_function=act,
+                                   message_aggregation_function=p["message_aggregation_function"],
+                                   use_target_state_as_input=p["use_target_state_as_input"],
+                                   num_edge_MLP_hidden_layers=p["graph_num_edge_MLP_hidden_layers"],
+                                   num_aggr_MLP_hidden_layers=p["graph_num_aggr_MLP_hidden_layers"], weights=w)
+
+    # ---- models/sparse_graph_model.py:162-202 ----
+    def node_representations(self, features, plan: GraphPlan, num_incoming):
+        p = self.params
+        act = _ACT[p["graph_model_activation_function"].lower() if p["graph_model_activation_function"] else None]
+        cur = features if self.projection is None else act(_matmul(features, self.projection))
+        last_residual = torch.zeros_like(cur)
+        keep = p["graph_layer_input_dropout_keep_prob"]
+        for l, w in enumerate(self.layers):
+            if self.training and keep < 1.0:
+                cur = torch.nn.functional.dropout(cur, p=1.0 - keep)
+            if l % p["graph_residual_connection_every_num_layers"] == 0:
+                t = cur
+                if l > 0:
+                    cur = (cur + last_residual) / 2
+                last_residual = t
+            cur = self._apply_gnn_layer(cur, plan, num_incoming, w)
+            if "inter_ln_gamma" in w:
+                cur = torch.nn.functional.layer_norm(cur, (p["hidden_size"],), w["inter_ln_gamma"], w["inter_ln_beta"], 1e-12)
+            if "inter_dense" in w:
+                cur = act(_matmul(cur, w["inter_dense"]))
+        return cur
+
+    def forward(self, features, plan, num_incoming, graph_nodes_list=None, num_graphs: Optional[int] = None):
+        """PPI: per-node logits [V, num_labels].  QM9: per-graph outputs [len(task_ids), G] (tasks/qm9_task.py:178-189)."""
+        final = self.node_representations(features, plan, num_incoming)
+        if self.task == "ppi":
+            return _matmul(final, self.head["kernel"]) + self.head["bias"]
+        gate_in = torch.cat([final, features], dim=-1)
+        outs = []
+        for hd in self.head:
+            per_node = _matmul(final, hd["kernel"]) + hd["bias"]
+            gated = torch.sigmoid(_matmul(gate_in, hd["gate_kernel"]) + hd["gate_bias"]) * per_node
+            outs.append(torch.zeros((int(num_graphs), 1), dtype=torch.float32, device=final.device)
+                        .index_add(0, graph_nodes_list.long(), gated).squeeze(-1))
+        return torch.stack(outs)
+
+    def task_metrics(self, outputs, targets) -> Dict[str, torch.Tensor]:
+        if self.task == "ppi":
+            return RGCNPPIModel.task_metrics(self, outputs, targets)
+        err = outputs - targets                                                  # [tasks, G]
+        m = {"abs_err_task%d" % t: err[i].abs().sum() for i, t in enumerate(self.task_ids)}
+        m["loss"] = (0.5 * err * err).mean(dim=1).sum()                           # tasks/qm9_task.py:195-197
+        m["total_loss"] = m["loss"] * outputs.shape[1]
+        return m
+
+    make_optimizer = RGCNPPIModel.make_optimizer
+    clip_gradients_ = RGCNPPIModel.clip_gradients_
+
+    def train_step_async(self, optimizer, features, plan, num_incoming, targets, graph_nodes_list=None,
+                         num_graphs: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        self.train()
+        optimizer.zero_grad(set_to_none=True)
+        m = self.task_metrics(self(features, plan, num_incoming, graph_nodes_list, num_graphs), targets)
+        m["loss"].backward()
+        self.clip_gradients_()
+        optimizer.step()
+        return {k: v.detach() for k, v in m.items()}
+
+    def train_step(self, optimizer, features, plan, num_incoming, targets, graph_nodes_list=None,
+                   num_graphs: Optional[int] = None) -> Dict[str, float]:
+        m = self.train_step_async(optimizer, features, plan, num_incoming, targets, graph_nodes_list, num_graphs)
+        keys = list(m)
+        return dict(zip(keys, torch.stack([m[k].float() for k in keys]).tolist()))
+
+    # ---- reference snapshots ----
+    def load_reference_weights(self, weights: Dict[str, np.ndarray]) -> List[str]:
+        """Assign a reference snapshot by tf variable name (checkpoint.sort_variables); the per-layer dictionaries of
+        the snapshot and of this model use the same keys.  Raises when a parameter has no saved value / another shape."""
+        from .checkpoint import scaffold_variables, sort_variables, split_layer_norms
+        srt = sort_variables(weights)
+        T = self.params["graph_num_timesteps_per_layer"] if self.kind in _LAYERS_WITH_OWN_LN else 0
+        by_index = {i: split_layer_norms(l, T) for i, l in zip(srt["layer_indices"], srt["layers"])}
+        outside = scaffold_variables(srt["outside"], self.feature_size, self.params["hidden_size"])
+
+        def assign(dst, src, path):
+            if isinstance(dst, dict):
+                for k, v in dst.items():
+                    if k == "kind" or v is None:
+                        continue
+                    if not isinstance(src, dict) or k not in src:
+                        raise KeyError("reference snapshot has no value for %s.%s" % (path, k))
+                    assign(v, src[k], "%s.%s" % (path, k))
+            elif isinstance(dst, (list, tuple)):
+                if not isinstance(src, (list, tuple)) or len(src) != len(dst):
+                    raise KeyError("reference snapshot: %s needs %d entries" % (path, len(dst)))
+                for i, v in enumerate(dst):
+                    assign(v, src[i], "%s.%d" % (path, i))
+            else:
+                a = np.asarray(src, dtype=np.float32)
+                if tuple(a.shape) != tuple(dst.shape):
+                    raise ValueError("%s: snapshot shape %s != model shape %s" % (path, a.shape, tuple(dst.shape)))
+                with torch.no_grad():
+                    dst.copy_(torch.as_tensor(a))
+
+        if self.projection is not None:
+            if "projection" not in outside:
+                raise KeyError("reference snapshot has no input projection kernel")
+            assign(self.projection, outside["projection"], "projection")
+        for l, w in enumerate(self.layers):
+            if l not in by_index:
+                raise KeyError("reference snapshot has no variables for gnn_layer_%d" % l)
+            assign(w, by_index[l], "gnn_layer_%d" % l)
+        if self.task == "ppi":
+            heads = [h for h in outside["head"] if "bias" in h]
+            if not heads:
+                raise KeyError("reference snapshot has no output layer")
+            assign(self.head, heads[-1], "head")
+        return list(srt["unused"])
