@@ -43,3 +43,29 @@ print(json.dumps({"model": "RGCN PPI hidden=256 3 layers (699,257 params)", "V":
                   "train_step_ms": ms_train, "train_edges_per_s": b.num_edges / (ms_train * 1e-3),
                   "eval_forward_ms": ms_eval, "eval_edges_per_s": b.num_edges / (ms_eval * 1e-3),
                   "reference_readme_v100": {"train_edges_per_s": 1952084, "valid_edges_per_s": 3098674}}))
+
+# ---- the other families through the general scaffold: QM9-shaped batch (2,000 molecule graphs), hidden 128, 2 layers ----
+from tf_gnn_samples_b200.scaffold import SparseGraphModel
+qb = batching.qm9_like_batch(num_graphs=2000, seed=1, add_self_loop_edges=True)
+qplan = G.GraphPlan(qb.adjacency_lists, qb.num_nodes, device=dev)
+qfeats = torch.as_tensor(qb.node_features).to(dev)
+qcnt = torch.as_tensor(qb.type_to_num_incoming_edges).to(dev)
+sizes = np.diff(qb.graph_node_offsets)
+gl = torch.as_tensor(np.repeat(np.arange(qb.num_graphs), sizes)).to(dev)
+tg = torch.randn((1, qb.num_graphs), device=dev)
+rows = {}
+for kind in ["ggnn", "rgat", "rgin", "gnn-edge-mlp", "gnn-film", "rgcn"]:
+    m = SparseGraphModel(kind, "qm9", num_edge_types=5, feature_size=15, device=dev,
+                         params={"graph_num_layers": 2, "graph_layer_input_dropout_keep_prob": 1.0,
+                                 "graph_num_timesteps_per_layer": 4 if kind == "ggnn" else 1})
+    o = m.make_optimizer()
+    def fwd_q():
+        m.eval()
+        with torch.no_grad():
+            return m(qfeats, qplan, qcnt, gl, qb.num_graphs)
+    t_train = timed(lambda: m.train_step_async(o, qfeats, qplan, qcnt, tg, gl, qb.num_graphs), n=20)
+    t_eval = timed(fwd_q, n=20)
+    rows[kind] = {"train_step_ms": t_train, "eval_forward_ms": t_eval, "train_edges_per_s": qb.num_edges / (t_train * 1e-3),
+                  "eval_edges_per_s": qb.num_edges / (t_eval * 1e-3)}
+print(json.dumps({"qm9_shaped": {"graphs": qb.num_graphs, "V": qb.num_nodes, "M": qb.num_edges, "L": 5, "hidden": 128,
+                                 "layers": 2, "models": rows}}))
