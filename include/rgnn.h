@@ -64,7 +64,8 @@ enum rgnn_aggregation { RGNN_AGG_SUM = 0, RGNN_AGG_MAX = 1, RGNN_AGG_MEAN = 2, R
 enum rgnn_cell { RGNN_CELL_RNN = 0, RGNN_CELL_GRU = 1 };
 enum rgnn_layer_kind {
   RGNN_LAYER_RGCN = 0, RGNN_LAYER_GGNN = 1, RGNN_LAYER_RGAT = 2, RGNN_LAYER_FILM = 3,
-  RGNN_LAYER_EDGE_MLP = 4, RGNN_LAYER_RGIN = 5, RGNN_LAYER_RGCN_BACKWARD = 6
+  RGNN_LAYER_EDGE_MLP = 4, RGNN_LAYER_RGIN = 5, RGNN_LAYER_RGCN_BACKWARD = 6,
+  RGNN_LAYER_RGDCN = 7   /* rgnn_workspace_bytes: pass channel_dim as mlp_layers */
 };
 
 typedef struct rgnn_plan rgnn_plan_t;
@@ -196,6 +197,18 @@ RGNN_API int rgnn_rgin_forward(const rgnn_plan_t* plan, const float* node_embedd
                       const float* ln_gamma, const float* ln_beta,
                       int activation, int aggregation, int use_target_state_as_input, int num_timesteps,
                       float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* gnns/rgdcn.py:8-171 -- relational graph DYNAMIC convolution: the state is split into num_channels channels of
+ * K = d / num_channels; message of edge (u -> v, type l), channel c:  h_u[c,:] . W[v,l,c]  with the K x K kernel
+ * W[v,l,c] = reshape(act(F_{l,c} . x_v)), x_v = h_v (use_full_state) or h_v[c,:]; then 1/(c+1e-7) scaling, aggregation over
+ * all types, activation.  channel_weights: host array of L*num_channels device pointers, entry l*num_channels + c =
+ * F_{l,c} [d or K, K*K] (Keras Dense kernel; tie_channel_weights = the same pointer for every c).  K must be a power of
+ * two in [4, 128], d <= 512.  For sum / mean / sqrt_n the per-(target, type) source rows are summed before ONE matvec per
+ * channel (the kernel depends on the target only); max applies it per edge. */
+RGNN_API int rgnn_rgdcn_forward(const rgnn_plan_t* plan, const float* h, int32_t d, int32_t num_channels,
+                       const float* const* channel_weights, int use_full_state, const float* num_incoming,
+                       int activation, int aggregation, int normalize, int num_timesteps, float* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- building blocks exported for tests / other hosts ---------------------------------------
  * utils/utils.py:23-33: aggregate `data` [M, d] (rows in the ORIGINAL type-major message order)

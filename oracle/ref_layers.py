@@ -420,6 +420,44 @@ def sparse_rgin_layer(node_embeddings, adjacency_lists, state_dim, num_timesteps
     return cur
 
 
+# --------------------------------------------------------------------------------------
+# gnns/rgdcn.py:8-171
+# --------------------------------------------------------------------------------------
+def sparse_rgdcn_layer(node_embeddings, adjacency_lists, type_to_num_incoming_edges, num_channels=8, channel_dim=16,
+                       num_timesteps=1, use_full_state_for_channel_weights=False, tie_channel_weights=False,
+                       activation_function="tanh", message_aggregation_function="sum", normalize_by_num_incoming=True,
+                       *, weights: Dict, dtype=np.float64):
+    """weights: {"channel_weights": L x C' x [D or K, K*K]}, C' = 1 when tied (rgdcn.py:96-107) else num_channels."""
+    h, adj = _prep(node_embeddings, adjacency_lists, dtype)
+    num_nodes = h.shape[0]                                                    # rgdcn.py:88
+    activation_fn = get_activation(activation_function)                        # :92
+    aggregation_fn = get_aggregation_function(message_aggregation_function)   # :93
+    message_targets = np.concatenate([a[:, 1] for a in adj])                  # :113
+    cnt = np.asarray(type_to_num_incoming_edges).astype(dtype) if type_to_num_incoming_edges is not None else None
+    C, K = num_channels, channel_dim
+    cur = h
+    for _ in range(num_timesteps):                                            # :116
+        chunked = cur.reshape(-1, C, K)                                       # :117-118
+        new_chunks = []
+        for c in range(C):                                                    # :121
+            chan = chunked[:, c, :]                                           # :122
+            per_type = []
+            for l, a in enumerate(adj):                                       # :126
+                src, tgt = a[:, 0], a[:, 1]
+                src_states = chan[src]                                        # :129-131
+                inp = cur if use_full_state_for_channel_weights else chan     # :133-136
+                kernel = weights["channel_weights"][l][0 if tie_channel_weights else c]      # :139
+                ew = _apply_act(activation_fn, dense(inp, kernel)).reshape(-1, K, K)       # :140-141 (Dense carries the activation)
+                msgs = np.einsum('vi,vij->vj', src_states, ew[tgt])                        # :142-146
+                if normalize_by_num_incoming:                                 # :147-151
+                    msgs = (dtype(1.0) / (cnt[l][tgt] + dtype(SMALL_NUMBER)))[:, None] * msgs
+                per_type.append(msgs)
+            agg = aggregation_fn(np.concatenate(per_type, axis=0), message_targets, num_nodes)   # :155-159
+            new_chunks.append(_apply_act(activation_fn, agg))                 # :160
+        cur = np.concatenate(new_chunks, axis=1)                              # :164-165
+    return cur
+
+
 LAYERS = {
     "rgcn": sparse_rgcn_layer,
     "ggnn": sparse_ggnn_layer,
@@ -427,6 +465,7 @@ LAYERS = {
     "gnn-film": sparse_gnn_film_layer,
     "gnn-edge-mlp": sparse_gnn_edge_mlp_layer,
     "rgin": sparse_rgin_layer,
+    "rgdcn": sparse_rgdcn_layer,
 }
 
 

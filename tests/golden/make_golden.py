@@ -46,6 +46,8 @@ CASES = {
                          kw=dict(state_dim=D, activation_function="gelu", num_edge_hidden_layers=1)),
     "rgin": dict(fn="rgin", wfn=lambda: W.rgin_weights(4, D, D, num_aggr_MLP_hidden_layers=1, random_ln=True), indeg=False,
                  kw=dict(state_dim=D, activation_function="ReLU", num_edge_MLP_hidden_layers=1, num_aggr_MLP_hidden_layers=1)),
+    "rgdcn": dict(fn="rgdcn", wfn=lambda: W.rgdcn_weights(4, 4, 8, stddev=0.15), indeg=True,
+                  kw=dict(num_channels=4, channel_dim=8, num_timesteps=2, activation_function="tanh")),
 }
 
 

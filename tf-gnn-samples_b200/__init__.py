@@ -8,6 +8,6 @@ from .utils import (SMALL_NUMBER, BIG_NUMBER, get_activation, get_aggregation_fu
                     get_gated_unit)
 from .engine import GraphPlan, RgnnError, launch_count, set_weight_cache, weight_cache_clear  # noqa: F401
 from .gnns import (sparse_rgcn_layer, sparse_ggnn_layer, sparse_rgat_layer, sparse_rgin_layer,  # noqa: F401
-                   sparse_gnn_edge_mlp_layer, sparse_gnn_film_layer, rgcn_layer_stack)
+                   sparse_gnn_edge_mlp_layer, sparse_gnn_film_layer, sparse_rgdcn_layer, rgcn_layer_stack)
 
 __version__ = "0.1.0"

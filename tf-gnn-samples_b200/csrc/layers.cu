@@ -279,6 +279,7 @@ extern "C" size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, 
       floats = V * 2 * L * dm * (nl + 1) + M * dm * (nl + 1) + (4 + nl) * V * dm;
       break;
     }
+    case RGNN_LAYER_RGDCN: floats = V * L * dm * (size_t)(mlp_layers > 0 ? mlp_layers : 16) + 2 * V * dm; break;   // mlp_layers carries channel_dim
     default: return 0;
   }
   // scratch for the pre-swizzled hi/lo weight images of the largest dense contraction of the layer
@@ -435,6 +436,55 @@ extern "C" int rgnn_rgcn_stack_forward(const rgnn_plan_t* plan, const float* h, 
     float* dst = (l == num_layers - 1) ? out : buf[l & 1];
     RGNN_PROPAGATE(rgnn_rgcn_forward(plan, cur, d, d, edge_weights + (size_t)l * plan->L, num_incoming, activation,
                                      aggregation, normalize, 0, 1, dst, inner, inner_bytes, stream_));
+    cur = dst;
+  }
+  return RGNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gnns/rgdcn.py:8-171
+// ---------------------------------------------------------------------------------------------
+extern "C" int rgnn_rgdcn_forward(const rgnn_plan_t* plan, const float* h, int32_t d, int32_t num_channels,
+                                  const float* const* channel_weights, int use_full_state, const float* num_incoming,
+                                  int activation, int aggregation, int normalize, int num_timesteps, float* out,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_PROPAGATE(check_common(plan, h, d, d, out, num_timesteps, "rgdcn"));
+  RGNN_PROPAGATE(check_act(activation, "rgdcn"));
+  RGNN_PROPAGATE(check_agg(aggregation, "rgdcn"));
+  RGNN_REQUIRE(channel_weights != nullptr, "rgdcn: channel_weights is NULL");
+  RGNN_REQUIRE(num_channels >= 1 && num_channels <= RGNN_MAX_EDGE_TYPES && (d % num_channels) == 0,
+               "rgdcn: num_channels %d must divide the state dim %d (and be <= %d)", num_channels, d, RGNN_MAX_EDGE_TYPES);
+  RGNN_REQUIRE(!normalize || num_incoming != nullptr, "rgdcn: normalize_by_num_incoming needs type_to_num_incoming_edges");
+  const int V = plan->V, L = plan->L, C = num_channels, K = d / num_channels;
+  RGNN_REQUIRE(K >= 4 && (K & (K - 1)) == 0 && K <= 128, "rgdcn: channel_dim %d must be a power of two in [4, 128]", K);
+  for (int i = 0; i < L * C; ++i)
+    RGNN_REQUIRE(channel_weights[i] != nullptr && aligned16(channel_weights[i]), "rgdcn: channel weight %d is NULL / misaligned", i);
+  Arena ar(workspace, workspace_bytes);
+  float* wdyn = ar.floats((size_t)V * L * d * K);
+  float* buf[2] = {nullptr, nullptr};
+  if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * d); buf[1] = ar.floats((size_t)V * d); }
+  RGNN_PROPAGATE(check_ws(ar, "rgdcn"));
+  const float* cur = h;
+  for (int t = 0; t < num_timesteps; ++t) {
+    float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
+    // W[v, l, c] = act(F_{l,c} . input_v) reshaped [K, K]  (:139-148; the Dense carries the layer's activation, :101-103)
+    for (int l = 0; l < L; ++l) {
+      GemmParams g;
+      g.A1 = cur; g.lda1 = d; g.M = V; g.N = K * K; g.ldb1 = K * K;
+      g.C = wdyn + (size_t)l * d * K; g.ldc = L * d * K;
+      g.act = activation; g.batch = C;
+      for (int c = 0; c < C; ++c) { g.bptr[c] = channel_weights[l * C + c]; g.bptr2[c] = nullptr; }
+      if (use_full_state) { g.K1 = d; g.batch_mode = BATCH_SHARED_A; }       // input = the whole state h_v
+      else { g.K1 = K; g.batch_mode = BATCH_COL_BLOCKS; }                    // input = the channel's slice h_v[c]
+      RGNN_PROPAGATE(run_gemm(g, ar, stream));
+    }
+    RgdcnParams r;
+    r.V = V; r.L = L; r.D = d; r.K = K;
+    r.seg_off = plan->seg_off; r.e_src = plan->e_src; r.e_type = plan->e_type;
+    r.h = cur; r.wdyn = wdyn; r.num_incoming = normalize ? num_incoming : nullptr;
+    r.agg = aggregation; r.act_out = activation; r.out = dst;
+    RGNN_PROPAGATE(launch_rgdcn_edges(r, stream));
     cur = dst;
   }
   return RGNN_OK;

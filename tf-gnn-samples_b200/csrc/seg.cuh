@@ -53,6 +53,22 @@ struct RgatParams {
 };
 int launch_seg_rgat(const RgatParams& p, cudaStream_t stream);
 
+// gnns/rgdcn.py:121-171: messages h_u[c,:] . W[v,l,c] with a per-(target, type, channel) K x K kernel computed from the
+// target's state.  wdyn [V, L, C, K, K] row-major (C = D / K).
+struct RgdcnParams {
+  int V = 0, L = 1, D = 0, K = 0;
+  const int32_t* seg_off = nullptr;
+  const int32_t* e_src = nullptr;
+  const int32_t* e_type = nullptr;
+  const float* h = nullptr;            // [V, D]
+  const float* wdyn = nullptr;         // [V, L, D * K]
+  const float* num_incoming = nullptr; // [L, V] or NULL
+  int agg = RGNN_AGG_SUM;
+  int act_out = RGNN_ACT_LINEAR;
+  float* out = nullptr;                // [V, D]
+};
+int launch_rgdcn_edges(const RgdcnParams& p, cudaStream_t stream);
+
 struct AttnTable { const float* att[RGNN_MAX_EDGE_TYPES]; };
 // s_src[n,l,k] = <att_l[k*2d : k*2d+d], T[n,l,k*d:(k+1)*d]>, s_tgt with att_l[k*2d+d : (k+1)*2d]  (rgat.py:106-115)
 int launch_rgat_scores(const float* table, int V, int L, int D, int K, const AttnTable& att, float* s_src,

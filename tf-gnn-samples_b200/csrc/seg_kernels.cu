@@ -226,6 +226,94 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_heavy_kernel(
   }
 }
 
+// ---- RGDCN (gnns/rgdcn.py:121-171): per-channel K x K kernels that depend on the TARGET ----------------------
+// One warp per target; lane owns NV float4 of the D = C*K state (column 4*lane + 128*k), i.e. 4 outputs j0..j0+3 of
+// one channel c.  The K/4 lanes of a channel are consecutive (K is a power of two <= 128), so the K inputs of the
+// channel's matvec are exchanged with shuffles inside that lane group.
+//   sum / mean / sqrt_n: every message of a (target, type) run shares W[v, l] and the scale, so the raw source rows
+//     are summed first (one gather-add per edge, like the RGCN edge stage) and ONE K x K matvec per channel is applied
+//     per run:  sum_u s (h_u[c] . W) = (s sum_u h_u[c]) . W;
+//   max: the message itself is needed per edge -> matvec per edge (W rows come from L1).
+template <int NV>
+__device__ __forceinline__ void rgdcn_apply(const RgdcnParams& p, int v, int ty, int lane, int gbase, const bool (&ok)[NV],
+                                            const float4 (&x)[NV], float scale, float4 (&m)[NV]) {
+  const int K = p.K;
+  const float* wrow = p.wdyn + ((size_t)v * p.L + ty) * ((size_t)p.D * K);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    m[k] = f4(0.0f);
+    const int col = lane * 4 + k * 128;
+    const float* wc = wrow + (size_t)(col / K) * K * K + (col % K);   // W[v, l, c, i, j0..j0+3] = wc[i * K]
+    for (int q = 0; q < K / 4; ++q) {
+      const float x0 = __shfl_sync(0xffffffffu, x[k].x, gbase + q), x1 = __shfl_sync(0xffffffffu, x[k].y, gbase + q);
+      const float x2 = __shfl_sync(0xffffffffu, x[k].z, gbase + q), x3 = __shfl_sync(0xffffffffu, x[k].w, gbase + q);
+      if (ok[k]) {
+        const float4 w0 = ldg4(wc + (size_t)(4 * q) * K), w1 = ldg4(wc + (size_t)(4 * q + 1) * K);
+        const float4 w2 = ldg4(wc + (size_t)(4 * q + 2) * K), w3 = ldg4(wc + (size_t)(4 * q + 3) * K);
+        m[k].x = fmaf(x0, w0.x, m[k].x); m[k].y = fmaf(x0, w0.y, m[k].y); m[k].z = fmaf(x0, w0.z, m[k].z); m[k].w = fmaf(x0, w0.w, m[k].w);
+        m[k].x = fmaf(x1, w1.x, m[k].x); m[k].y = fmaf(x1, w1.y, m[k].y); m[k].z = fmaf(x1, w1.z, m[k].z); m[k].w = fmaf(x1, w1.w, m[k].w);
+        m[k].x = fmaf(x2, w2.x, m[k].x); m[k].y = fmaf(x2, w2.y, m[k].y); m[k].z = fmaf(x2, w2.z, m[k].z); m[k].w = fmaf(x2, w2.w, m[k].w);
+        m[k].x = fmaf(x3, w3.x, m[k].x); m[k].y = fmaf(x3, w3.y, m[k].y); m[k].z = fmaf(x3, w3.z, m[k].z); m[k].w = fmaf(x3, w3.w, m[k].w);
+      }
+    }
+    m[k] = mul4(m[k], scale);
+  }
+}
+
+template <int NV, bool MAXAGG>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) rgdcn_edge_kernel(const __grid_constant__ RgdcnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (v >= p.V) return;
+  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  const int gbase = lane - ((lane * 4) % p.K) / 4;     // first lane of this lane's channel group (128 % K == 0)
+  bool ok[NV];
+  float4 acc[NV], run[NV], m[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ok[k] = (lane * 4 + k * 128) < p.D;
+    acc[k] = f4(MAXAGG ? -FLT_MAX : 0.0f);
+    run[k] = f4(0.0f);
+  }
+  int cur_type = -1;
+  auto scale_of = [&](int ty) { return p.num_incoming != nullptr ? 1.0f / (__ldg(p.num_incoming + (size_t)ty * p.V + v) + 1e-7f) : 1.0f; };
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int n = min(32, end - e0);
+    int my_src = 0, my_type = 0;
+    if (lane < n) { my_src = __ldg(p.e_src + e0 + lane); my_type = __ldg(p.e_type + e0 + lane); }
+    for (int j = 0; j < n; ++j) {
+      const int src = __shfl_sync(0xffffffffu, my_src, j), ty = __shfl_sync(0xffffffffu, my_type, j);
+      float4 r[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) r[k] = ok[k] ? ldg4(p.h + (size_t)src * p.D + lane * 4 + k * 128) : f4(0.0f);
+      if (MAXAGG) {
+        rgdcn_apply<NV>(p, v, ty, lane, gbase, ok, r, scale_of(ty), m);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = max4(acc[k], m[k]);
+      } else {
+        if (ty != cur_type) {                            // warp-uniform: close the previous (v, type) run
+          if (cur_type >= 0) {
+            rgdcn_apply<NV>(p, v, cur_type, lane, gbase, ok, run, scale_of(cur_type), m);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) { acc[k] = add4(acc[k], m[k]); run[k] = f4(0.0f); }
+          }
+          cur_type = ty;
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) run[k] = add4(run[k], r[k]);
+      }
+    }
+  }
+  if (!MAXAGG && cur_type >= 0) {
+    rgdcn_apply<NV>(p, v, cur_type, lane, gbase, ok, run, scale_of(cur_type), m);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = add4(acc[k], m[k]);
+  }
+  SegParams f;
+  f.D = p.D; f.agg = p.agg; f.act_out = p.act_out; f.out = p.out; f.ld_out = p.D;
+  seg_finish<NV>(f, v, 0, lane, ok, end - beg, acc);
+}
+
 // ---- RGAT: per-target, per-head online softmax fused with the weighted sum -----------------
 template <int NV>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __grid_constant__ RgatParams p) {
@@ -573,6 +661,27 @@ int launch_seg_rgat(const RgatParams& p, cudaStream_t stream) {
   // one warp per 128-column slice of a target row (heads are independent; more resident warps win here)
   const dim3 grid((p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (p.D + 127) / 128);
   seg_rgat_kernel<1><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  RGNN_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return RGNN_OK;
+}
+
+int launch_rgdcn_edges(const RgdcnParams& p, cudaStream_t stream) {
+  RGNN_REQUIRE(p.D > 0 && p.K >= 4 && (p.K & (p.K - 1)) == 0 && p.K <= 128 && (p.D % p.K) == 0,
+               "rgdcn: channel_dim %d must be a power of two in [4, 128] dividing the state dim %d", p.K, p.D);
+  if (p.D > RGNN_MAX_STATE_DIM) {
+    set_error("rgdcn: state dim %d > %d is not supported in this build", p.D, RGNN_MAX_STATE_DIM);
+    return RGNN_E_UNSUPPORTED;
+  }
+  if (p.V == 0) return RGNN_OK;
+  const unsigned gx = (p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  const bool mx = p.agg == RGNN_AGG_MAX;
+  switch (nv_for(p.D)) {
+    case 1: if (mx) rgdcn_edge_kernel<1, true><<<gx, WARPS_PER_BLOCK * 32, 0, stream>>>(p); else rgdcn_edge_kernel<1, false><<<gx, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    case 2: if (mx) rgdcn_edge_kernel<2, true><<<gx, WARPS_PER_BLOCK * 32, 0, stream>>>(p); else rgdcn_edge_kernel<2, false><<<gx, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    case 3: if (mx) rgdcn_edge_kernel<3, true><<<gx, WARPS_PER_BLOCK * 32, 0, stream>>>(p); else rgdcn_edge_kernel<3, false><<<gx, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+    default: if (mx) rgdcn_edge_kernel<4, true><<<gx, WARPS_PER_BLOCK * 32, 0, stream>>>(p); else rgdcn_edge_kernel<4, false><<<gx, WARPS_PER_BLOCK * 32, 0, stream>>>(p); break;
+  }
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return RGNN_OK;

@@ -12,7 +12,7 @@ SMALL_NUMBER = 1e-7   # utils/utils.py:7  (baked into the kernels as 1e-7f)
 ACT_LINEAR, ACT_TANH, ACT_RELU, ACT_LEAKY_RELU, ACT_ELU, ACT_SELU, ACT_GELU = range(7)
 AGG_SUM, AGG_MAX, AGG_MEAN, AGG_SQRT_N = range(4)
 CELL_RNN, CELL_GRU = range(2)
-LAYER_RGCN, LAYER_GGNN, LAYER_RGAT, LAYER_FILM, LAYER_EDGE_MLP, LAYER_RGIN, LAYER_RGCN_BACKWARD = range(7)
+LAYER_RGCN, LAYER_GGNN, LAYER_RGAT, LAYER_FILM, LAYER_EDGE_MLP, LAYER_RGIN, LAYER_RGCN_BACKWARD, LAYER_RGDCN = range(8)
 
 _ACTIVATIONS = {"linear": ACT_LINEAR, "tanh": ACT_TANH, "relu": ACT_RELU, "leaky_relu": ACT_LEAKY_RELU,
                 "elu": ACT_ELU, "selu": ACT_SELU, "gelu": ACT_GELU}

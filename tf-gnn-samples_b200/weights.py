@@ -91,6 +91,18 @@ def rgin_weights(L: int, d_in: int, d_out: int, num_edge_MLP_hidden_layers: Opti
     return w
 
 
+def rgdcn_weights(L: int, num_channels: int, channel_dim: int, use_full_state: bool = False, tie_channel_weights: bool = False,
+                  seed: int = 2, stddev: Optional[float] = None) -> Dict:
+    """gnns/rgdcn.py:97-104: per (edge type, channel) a bias-free Dense [D or K, K*K], truncated-normal initialised with
+    stddev 1/K^2 (pass a larger ``stddev`` in tests so that the dynamic kernels are not vanishingly small)."""
+    rng = np.random.default_rng(seed + 6000)
+    rows = num_channels * channel_dim if use_full_state else channel_dim
+    sd = 1.0 / (channel_dim ** 2) if stddev is None else stddev
+    def one():
+        return np.clip(rng.standard_normal((rows, channel_dim * channel_dim)), -2.0, 2.0).astype(np.float32) * np.float32(sd)
+    return {"channel_weights": [[one() for _ in range(1 if tie_channel_weights else num_channels)] for _ in range(L)]}
+
+
 def to_torch(weights, device):
     """Recursively move a weight dict (numpy arrays) to float32 tensors on ``device``."""
     import torch
