@@ -56,6 +56,10 @@ def apply_gnn_layer(kind, cur, adjacency_lists, type_to_num_incoming_edges, para
                                    message_aggregation_function=agg, use_target_state_as_input=params["use_target_state_as_input"],
                                    num_edge_MLP_hidden_layers=params["graph_num_edge_MLP_hidden_layers"],
                                    num_aggr_MLP_hidden_layers=params["graph_num_aggr_MLP_hidden_layers"], weights=w, dtype=dtype)
+    if kind == "rgdcn":                                                                             # rgdcn_model.py:34-52
+        return R.sparse_rgdcn_layer(cur, adjacency_lists, type_to_num_incoming_edges, params["num_channels"],
+                                    H // params["num_channels"], T, params["use_full_state_for_channel_weights"],
+                                    params["tie_channel_weights"], act, agg, weights=w, dtype=dtype)
     raise ValueError("Unknown model type '%s'" % kind)
 
 

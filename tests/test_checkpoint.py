@@ -41,6 +41,11 @@ def test_sorting_of_every_layer_family():
         "graph_model/gnn_layer_3/gru_cell/kernel:0": fake((64, 192), 20),
         "graph_model/gnn_layer_3/gru_cell/recurrent_kernel:0": fake((64, 192), 21),
         "graph_model/gnn_layer_3/gru_cell/bias:0": fake((192,), 22),
+        # layer 4: RGDCN
+        "graph_model/gnn_layer_4/Edge_0_Channel_0_Weight_Computation/kernel:0": fake((16, 256), 30),
+        "graph_model/gnn_layer_4/Edge_0_Channel_1_Weight_Computation/kernel:0": fake((16, 256), 31),
+        "graph_model/gnn_layer_4/Edge_1_Channel_0_Weight_Computation/kernel:0": fake((16, 256), 32),
+        "graph_model/gnn_layer_4/Edge_1_Channel_1_Weight_Computation/kernel:0": fake((16, 256), 33),
         # task head, optimizer slots, something unknown
         "out_layer_task/dense_1/kernel:0": fake((64, 121), 23),
         "out_layer_task/dense_1/bias:0": fake((121,), 24),
@@ -50,8 +55,10 @@ def test_sorting_of_every_layer_family():
         "graph_model/gnn_layer_0/Mystery/kernel:0": fake((3, 3), 27),
     }
     s = C.sort_variables(w)
-    assert s["layer_indices"] == [0, 1, 2, 3]
-    l0, l1, l2, l3 = s["layers"]
+    assert s["layer_indices"] == [0, 1, 2, 3, 4]
+    l0, l1, l2, l3, l4 = s["layers"]
+    assert [len(c) for c in l4["channel_weights"]] == [2, 2]
+    np.testing.assert_array_equal(l4["channel_weights"][1][0], w["graph_model/gnn_layer_4/Edge_1_Channel_0_Weight_Computation/kernel:0"])
     assert len(l0["edge_weights"]) == 2 and len(l0["attention"]) == 2 and l0["inter_dense"].shape == (64, 64)
     np.testing.assert_array_equal(l0["attention"][1], w["graph_model/gnn_layer_0/Edge_1_Attention_Parameters:0"])
     l1 = C.split_layer_norms(l1, num_timesteps=2)

@@ -35,7 +35,7 @@ def to_numpy(obj):
     return obj.detach().cpu().numpy()
 
 
-@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("kind", KINDS + ["rgdcn"])
 def test_whole_model_on_real_qm9_molecules(cuda_device, kind):
     import torch
     b, gl, tg, plan, feats, cnt, gl_d, tg_d = qm9_inputs(cuda_device)

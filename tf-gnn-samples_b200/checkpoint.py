@@ -10,7 +10,7 @@ This module reads such a pickle without TensorFlow, sorts the variables into the
 layer functions of ``gnns/`` take, and writes the same structure back.  Variable names follow the scopes the reference
 opens (``gnn_layer_%i`` models/sparse_graph_model.py:177; ``Edge_%i_Weight`` gnns/rgcn.py:74, ggnn.py:64, rgat.py:73,
 gnn_film.py:73; ``Edge_%i_Attention_Parameters`` rgat.py:76; ``Edge_%i_FiLM_Computations`` gnn_film.py:78;
-``Edge_%i_MLP`` gnn_edge_mlp.py:77, rgin.py:96; ``Aggregation_MLP`` rgin.py:81; ``Dense`` sparse_graph_model.py:199;
+``Edge_%i_MLP`` gnn_edge_mlp.py:77, rgin.py:96; ``Edge_%i_Channel_%i_Weight_Computation`` rgdcn.py:104; ``Aggregation_MLP`` rgin.py:81; ``Dense`` sparse_graph_model.py:199;
 Keras / tf.layers auto-names ``dense``, ``dense_1``, ``LayerNorm``, ``gru_cell``, ``simple_rnn_cell``).  TensorFlow is
 not available in this build environment, so the exact scope PREFIXES are unverified: matching is done
 on the ``gnn_layer_<i>`` component and the components after it, whatever precedes them, and every variable that was
@@ -94,6 +94,7 @@ def sort_variables(weights: Dict[str, np.ndarray]) -> Dict[str, Any]:
     Per layer the dictionary uses the keys of this package's layer functions:
       edge_weights / attention / film_weights           lists indexed by edge type
       edge_mlps                                         per edge type, kernels in creation order (dense, dense_1, ...)
+      channel_weights                                   per edge type, kernels indexed by channel (RGDCN)
       aggr_mlp                                          kernels in creation order
       ln_gamma / ln_beta                                lists indexed by timestep (LayerNorm, LayerNorm_1, ...)
       cell {"kind", "kernel", "recurrent_kernel", "bias"}
@@ -120,6 +121,10 @@ def sort_variables(weights: Dict[str, np.ndarray]) -> Dict[str, Any]:
         layer = layers.setdefault(int(m.group(2)), {})
         parts = m.group(3).split("/")
         head = parts[0]
+        cm = re.match(r"^Edge_(\d+)_Channel_(\d+)_Weight_Computation$", head)        # gnns/rgdcn.py:104
+        if cm and parts[1:] == ["kernel"]:
+            layer.setdefault("channel_weights", {}).setdefault(int(cm.group(1)), {})[int(cm.group(2))] = value
+            continue
         em = re.match(r"^Edge_(\d+)_(Weight|Attention_Parameters|FiLM_Computations|MLP)$", head)
         if em:
             t, kind = int(em.group(1)), em.group(2)
@@ -154,8 +159,9 @@ def sort_variables(weights: Dict[str, np.ndarray]) -> Dict[str, Any]:
         for key in ("edge_weights", "attention", "film_weights", "aggr_mlp", "ln_gamma", "ln_beta"):
             if key in layer:
                 layer[key] = as_list(layer[key])
-        if "edge_mlps" in layer:
-            layer["edge_mlps"] = [as_list(layer["edge_mlps"][t]) for t in sorted(layer["edge_mlps"])]
+        for key in ("edge_mlps", "channel_weights"):
+            if key in layer:
+                layer[key] = [as_list(layer[key][t]) for t in sorted(layer[key])]
         out_layers.append(layer)
     return {"layers": out_layers, "layer_indices": sorted(layers), "outside": outside, "unused": unused}
 

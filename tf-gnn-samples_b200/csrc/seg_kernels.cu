@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) rgdcn_edge_kernel(const 
   }
   SegParams f;
   f.D = p.D; f.agg = p.agg; f.act_out = p.act_out; f.out = p.out; f.ld_out = p.D;
-  seg_finish<NV>(f, v, 0, lane, ok, end - beg, acc);
+  seg_finish<NV>(f, v, lane * 4, lane, ok, end - beg, acc);   // col0 carries the lane's column offset
 }
 
 // ---- RGAT: per-target, per-head online softmax fused with the weighted sum -----------------

@@ -247,10 +247,13 @@ _MODEL_DEFAULTS = {                                            # <X>_Model.defau
                      "use_target_state_as_input": True, "num_edge_hidden_layers": 1},
     "gnn-film": {"hidden_size": 128, "graph_activation_function": "ReLU", "message_aggregation_function": "sum",
                  "normalize_messages_by_num_incoming": False},
+    "rgdcn": {"max_nodes_in_batch": 25000, "hidden_size": 128, "num_channels": 8, "use_full_state_for_channel_weights": False,
+              "tie_channel_weights": False, "graph_activation_function": "ReLU", "message_aggregation_function": "sum",
+              "graph_inter_layer_norm": True},
 }
 _MODEL_ALIASES = {"rgcn_model": "rgcn", "ggnn_model": "ggnn", "rgat_model": "rgat", "rgin_model": "rgin",
                   "gnn_edge_mlp": "gnn-edge-mlp", "gnn-edge_mlp": "gnn-edge-mlp", "gnn_edge_mlp_model": "gnn-edge-mlp",
-                  "gnn_film": "gnn-film", "gnn_film_model": "gnn-film"}
+                  "gnn_film": "gnn-film", "gnn_film_model": "gnn-film", "rgdcn_model": "rgdcn"}
 _LAYERS_WITH_OWN_LN = ("rgin", "gnn-edge-mlp", "gnn-film")      # one LayerNorm per timestep inside the layer function
 
 
@@ -294,6 +297,9 @@ class SparseGraphModel(torch.nn.Module):
                 w = W.rgat_weights(L, H, H, seed)
             elif self.kind == "gnn-film":
                 w = W.film_weights(L, H, H, seed, num_timesteps=T)
+            elif self.kind == "rgdcn":                          # channel_dim = hidden_size // num_channels (rgdcn_model.py:30-32)
+                w = W.rgdcn_weights(L, p["num_channels"], H // p["num_channels"], p["use_full_state_for_channel_weights"],
+                                    p["tie_channel_weights"], seed)
             elif self.kind == "gnn-edge-mlp":
                 w = W.edge_mlp_weights(L, H, H, p["num_edge_hidden_layers"], p["use_target_state_as_input"], seed, num_timesteps=T)
             else:
@@ -347,6 +353,11 @@ class SparseGraphModel(torch.nn.Module):
             return G.sparse_gnn_film_layer(cur, plan, cnt, H, num_timesteps=T, activation_function=act,
                                            message_aggregation_function=p["message_aggregation_function"],
                                            normalize_by_num_incoming=p["normalize_messages_by_num_incoming"], weights=w)
+        if self.kind == "rgdcn":                                  # inference only: the layer has no gradient path
+            return G.sparse_rgdcn_layer(cur, plan, cnt, p["num_channels"], H // p["num_channels"], num_timesteps=T,
+                                        use_full_state_for_channel_weights=p["use_full_state_for_channel_weights"],
+                                        tie_channel_weights=p["tie_channel_weights"], activation_function=act,
+                                        message_aggregation_function=p["message_aggregation_function"], weights=w)
         if self.kind == "gnn-edge-mlp":
             return G.sparse_gnn_edge_mlp_layer(cur, plan, cnt, H, num_timesteps=T, activation_function=act,
                                                message_aggregation_function=p["message_aggregation_function"],
