@@ -145,6 +145,8 @@ def test_fp32_reference_order_close_to_fp64_truth(name):
         w, args = W.film_weights(3, D, D), (indeg, D)
     elif name == "gnn-edge-mlp":
         w, args = W.edge_mlp_weights(3, D, D), (indeg, D)
+    elif name == "rgdcn":
+        w, args = W.rgdcn_weights(3, 4, 8, stddev=0.15), (indeg, 4, 8)
     else:
         w, args = W.rgin_weights(3, D, D), (D,)
     o64 = R.LAYERS[name](h, adj, *args, **kw, weights=w)
