@@ -87,3 +87,56 @@ def test_node_range_partition_halo_exchange_world2():
         assert err < 1e-9, "rank %d local result differs from global: %g" % (rank, err)
         assert edges_total == edges_batch                                # every edge owned by exactly one rank
         assert n_halo > 0 and n_own > 0
+
+
+def _ddp_worker(rank, world, port, ret):
+    """Data-parallel training host logic: shard the batch at graph boundaries, scale the local loss by the GLOBAL node
+    count, sum gradients with scaffold.all_reduce_gradients_ -> must equal the gradient on the union batch.  The layer
+    arithmetic is the float64 autograd oracle (CPU); the product's compute has no CPU path."""
+    from oracle import ref_autograd as A
+    from tf_gnn_samples_b200.scaffold import all_reduce_gradients_, global_count
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gs = [batching.make_ppi_like_graph(50 + 9 * i, 300, feature_dim=8, seed=20 + i) for i in range(4)]
+        full = batching.pack_batch(gs)
+        D = 8
+        w_np = W.rgcn_weights(3, D, D, seed=5)
+        labels_full = np.random.default_rng(6).standard_normal((full.num_nodes, D))
+
+        def loss_total(b, labels, weights):
+            out = A.sparse_rgcn_layer(torch.as_tensor(b.node_features, dtype=torch.float64), b.adjacency_lists,
+                                      torch.as_tensor(b.type_to_num_incoming_edges, dtype=torch.float64), weights=weights)
+            return ((out - torch.as_tensor(labels)) ** 2).sum()
+
+        # union-batch gradient (what one device computes): d (total / V) / d W
+        w_ref = A.to_torch64(w_np)
+        (loss_total(full, labels_full, w_ref) / full.num_nodes).backward()
+        # this rank's shard
+        shards = split_batch_by_graphs(full, world)
+        lo = sum(s.num_nodes for s in shards[:rank])
+        mine = shards[rank]
+        w_loc = A.to_torch64(w_np)
+        params = w_loc["edge_weights"] + [torch.zeros(3, dtype=torch.float64, requires_grad=True)]   # one parameter never touched locally
+        v_total = global_count(mine.num_nodes, torch.device("cpu"))
+        (loss_total(mine, labels_full[lo:lo + mine.num_nodes], w_loc) / v_total).backward()
+        all_reduce_gradients_(params)
+        err = max(float((p.grad - q.grad).abs().max() / q.grad.abs().max()) for p, q in zip(w_loc["edge_weights"], w_ref["edge_weights"]))
+        ret[rank] = (v_total, full.num_nodes, err, float(params[-1].grad.abs().max()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_data_parallel_gradient_sync_world2():
+    world, port = 2, free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ddp_worker, args=(world, port, ret), nprocs=world, join=True)
+        res = dict(ret)
+    assert set(res) == {0, 1}
+    for rank, (v_total, v_full, err, unused_grad) in res.items():
+        assert v_total == v_full
+        assert err < 1e-12, "rank %d: summed shard gradients differ from the union-batch gradient: %g" % (rank, err)
+        assert unused_grad == 0.0

@@ -44,6 +44,38 @@ def _matmul(x: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
     return y[:, :n] if pn else y
 
 
+def all_reduce_gradients_(parameters, group=None) -> None:
+    """Data-parallel training over graph-boundary shards: SUM the gradients of every parameter over the
+    ranks with ONE collective on a flattened buffer (NCCL on GPUs, gloo in the CPU tests).  Callers scale their local loss
+    by the GLOBAL normaliser (all nodes / all graphs of the union batch), so the sum is exactly the single-device gradient
+    of the union batch.  A parameter without a local gradient (e.g. the kernel of an edge type absent from this shard)
+    contributes zeros."""
+    import torch.distributed as dist
+    params = [q for q in parameters if q.requires_grad]
+    if not params or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for q in params:
+        if q.grad is None:
+            q.grad = torch.zeros_like(q)
+    flat = torch.cat([q.grad.reshape(-1) for q in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for q in params:
+        n = q.numel()
+        q.grad.copy_(flat[off:off + n].view_as(q.grad))
+        off += n
+
+
+def global_count(local_count: int, device, group=None) -> float:
+    """Sum of a per-rank count (nodes or graphs of the shard) over the ranks."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return float(local_count)
+    t = torch.tensor([float(local_count)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item())
+
+
 def rgcn_ppi_default_params() -> Dict:
     """Sparse_Graph_Model.default_params overlaid with RGCN_Model.default_params and the README's PPI run
     (hidden 256, 3 layers: README.md:29-35)."""
@@ -199,13 +231,20 @@ class RGCNPPIModel(torch.nn.Module):
         torch._foreach_mul_(scales, clip)
         torch._foreach_mul_(grads, scales)
 
-    def train_step_async(self, optimizer, features, plan, num_incoming, labels) -> Dict[str, torch.Tensor]:
+    def train_step_async(self, optimizer, features, plan, num_incoming, labels, group=None,
+                         global_num_nodes: Optional[float] = None) -> Dict[str, torch.Tensor]:
         """One step of __make_train_step: gradients of the per-node loss, per-tensor clip_by_norm, apply.  Nothing in
-        here waits for the device; the metrics come back as device tensors."""
+        here waits for the device; the metrics come back as device tensors.  With ``global_num_nodes`` (the node count of
+        the union batch over all ranks) the step is data-parallel: the local loss is total / global_num_nodes and the
+        gradients are summed over ``group`` before clipping, which reproduces the single-device step on the union batch."""
         self.train()
         optimizer.zero_grad(set_to_none=True)
         m = self.task_metrics(self(features, plan, num_incoming), labels)
-        m["loss"].backward()
+        if global_num_nodes is None:
+            m["loss"].backward()
+        else:
+            (m["total_loss"] / float(global_num_nodes)).backward()
+            all_reduce_gradients_(self.parameters(), group)
         self.clip_gradients_()
         optimizer.step()
         return {k: v.detach() for k, v in m.items()}
@@ -418,11 +457,17 @@ class SparseGraphModel(torch.nn.Module):
     clip_gradients_ = RGCNPPIModel.clip_gradients_
 
     def train_step_async(self, optimizer, features, plan, num_incoming, targets, graph_nodes_list=None,
-                         num_graphs: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                         num_graphs: Optional[int] = None, group=None, global_count_: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """``global_count_``: nodes (PPI) / graphs (QM9) of the union batch over all ranks -> data-parallel step
+        (see RGCNPPIModel.train_step_async)."""
         self.train()
         optimizer.zero_grad(set_to_none=True)
         m = self.task_metrics(self(features, plan, num_incoming, graph_nodes_list, num_graphs), targets)
-        m["loss"].backward()
+        if global_count_ is None:
+            m["loss"].backward()
+        else:
+            (m["total_loss"] / float(global_count_)).backward()      # total_loss = loss * local count for both heads
+            all_reduce_gradients_(self.parameters(), group)
         self.clip_gradients_()
         optimizer.step()
         return {k: v.detach() for k, v in m.items()}
