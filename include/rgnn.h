@@ -93,6 +93,12 @@ RGNN_API int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t num_
 RGNN_API int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t num_edge_types,
                         const int32_t* const* adjacency_lists, const int64_t* num_edges, int flags, void* stream);
 RGNN_API int rgnn_plan_status(const rgnn_plan_t* plan);
+/* Sharded execution (one rank of a node-range partition: owned nodes first, halo nodes after them): declare that only
+ * rows [0, num_targets) are targets whose outputs are wanted.  The edge stage then reduces only those rows and the
+ * TARGET-side node-level work of the layers (FiLM's gamma/beta GEMM, GGNN's cell) runs on them only; source-side transforms
+ * still cover all V rows.  Output rows >= num_targets are left untouched; layers must be called with num_timesteps == 1
+ * (halo states are refreshed by the caller's exchange between steps).  Default: num_targets = V. */
+RGNN_API int rgnn_plan_set_num_targets(rgnn_plan_t* plan, int32_t num_targets);
 RGNN_API int rgnn_plan_destroy(rgnn_plan_t* plan);
 RGNN_API int32_t rgnn_plan_num_nodes(const rgnn_plan_t* plan);
 RGNN_API int32_t rgnn_plan_num_edge_types(const rgnn_plan_t* plan);

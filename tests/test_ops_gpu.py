@@ -99,3 +99,31 @@ def test_layer_norm(cuda_device):
         g, b = rng.standard_normal(d).astype(np.float32), rng.standard_normal(d).astype(np.float32)
         got = ops.layer_norm(*(torch.as_tensor(t).to(cuda_device) for t in (x, g, b))).cpu().numpy()
         assert_parity(got, R.layer_norm(x.astype(np.float64), g, b), "layer_norm d=%d" % d, tol=1e-5)
+
+
+def test_restricted_target_rows_sharded_execution(cuda_device):
+    """rgnn_plan_set_num_targets: on a rank-local graph of a node-range partition (owned rows first, halo rows after)
+    restricting the target rows leaves the owned outputs bit-identical, for FiLM (gamma/beta GEMM on owned rows only),
+    GGNN (cell on owned rows only) and RGCN (edge stage only)."""
+    import torch
+    from tf_gnn_samples_b200 import (RgnnError, batching, sparse_ggnn_layer, sparse_gnn_film_layer, sparse_rgcn_layer, weights as W)
+    from tf_gnn_samples_b200.partition import NodeRangePartition
+    b = batching.varmisuse_like_batch(num_nodes=900, num_edges=14000, seed=5, feature_dim=8)
+    part = NodeRangePartition(b.adjacency_lists, b.type_to_num_incoming_edges, b.num_nodes, rank=1, world_size=3)
+    assert 0 < part.n_own < part.n_local
+    D, L = 64, len(b.adjacency_lists)
+    h = torch.as_tensor(np.tanh(np.random.default_rng(2).standard_normal((part.n_local, D))).astype(np.float32)).to(cuda_device)
+    cnt = torch.as_tensor(part.local_num_incoming).to(cuda_device)
+    full = GraphPlan(part.local_adjacency_lists, part.n_local, device=cuda_device)
+    own = GraphPlan(part.local_adjacency_lists, part.n_local, device=cuda_device).set_num_targets(part.n_own)
+    wf = W.to_torch(W.film_weights(L, D, D, random_ln=True), cuda_device)
+    wg = W.to_torch(W.ggnn_weights(L, D, random_bias=True), cuda_device)
+    wr = W.to_torch(W.rgcn_weights(L, D, D), cuda_device)
+    n = part.n_own
+    assert torch.equal(sparse_gnn_film_layer(h, full, cnt, D, weights=wf)[:n], sparse_gnn_film_layer(h, own, cnt, D, weights=wf)[:n])
+    assert torch.equal(sparse_ggnn_layer(h, full, D, weights=wg)[:n], sparse_ggnn_layer(h, own, D, weights=wg)[:n])
+    assert torch.equal(sparse_rgcn_layer(h, full, cnt, D, weights=wr)[:n], sparse_rgcn_layer(h, own, cnt, D, weights=wr)[:n])
+    with pytest.raises(RgnnError):                       # halo rows are not updated inside the call
+        sparse_ggnn_layer(h, own, D, num_timesteps=2, weights=wg)
+    with pytest.raises(RgnnError):
+        own.set_num_targets(part.n_local + 1)

@@ -55,6 +55,8 @@ int check_common(const rgnn_plan_t* plan, const float* h, int d_in, int d_out, c
   RGNN_REQUIRE(d_in > 0 && d_out > 0 && (d_in % 4) == 0 && (d_out % 4) == 0,
                "%s: state dims must be positive multiples of 4 (d_in=%d, d_out=%d)", who, d_in, d_out);
   RGNN_REQUIRE(num_timesteps >= 1, "%s: num_timesteps %d < 1", who, num_timesteps);
+  RGNN_REQUIRE(num_timesteps == 1 || plan->Vt == plan->V,
+               "%s: a plan restricted to %d of %d target rows supports num_timesteps == 1 only (halo rows are not updated)", who, plan->Vt, plan->V);
   RGNN_REQUIRE(num_timesteps == 1 || d_in == d_out,
                "%s: num_timesteps > 1 needs state_dim == input dim (d_in=%d, d_out=%d)", who, d_in, d_out);
   return RGNN_OK;
@@ -118,7 +120,7 @@ int gemm_shared_a(Arena& ar, const float* A, int V, int K, const float* const* B
 }
 
 void seg_from_plan(SegParams& s, const rgnn_plan_t* plan) {
-  s.V = plan->V; s.L = plan->L; s.scale_ld = plan->V;
+  s.V = plan->Vt; s.L = plan->L; s.scale_ld = plan->V;   // only the wanted target rows are reduced (rgnn_plan_set_num_targets)
   s.heavy_list = plan->heavy_list; s.heavy_count = plan->err_flag + 1;
   s.heavy_threshold = RGNN_HEAVY_SEGMENT; s.heavy_known = plan->num_heavy_host;
   s.seg_off = plan->seg_off; s.e_type = plan->e_type; s.e_idx = plan->e_src;
@@ -530,7 +532,7 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
     RGNN_PROPAGATE(launch_seg_reduce(s, stream));
     GemmParams g;
     g.A1 = m; g.lda1 = D; g.K1 = D;
-    g.M = V; g.bias = cell_bias;
+    g.M = plan->Vt; g.bias = cell_bias;   // the cell runs on the wanted target rows only
     if (cell_kind == RGNN_CELL_RNN) {                                         // SimpleRNNCell: act(x.W + b + h.U)
       g.A2 = cur; g.lda2 = D; g.K2 = D;
       g.B1 = cell_kernel; g.ldb1 = D; g.B2 = cell_recurrent_kernel; g.ldb2 = D;
@@ -545,7 +547,7 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
       GemmParams o;
       o.A1 = m; o.lda1 = D; o.K1 = D; o.A2 = rh; o.lda2 = D; o.K2 = D;
       o.B1 = cell_kernel + 2 * D; o.ldb1 = 3 * D; o.B2 = cell_recurrent_kernel + 2 * D; o.ldb2 = 3 * D;
-      o.M = V; o.N = D; o.bias = cell_bias + 2 * D; o.C = dst; o.ldc = D;
+      o.M = plan->Vt; o.N = D; o.bias = cell_bias + 2 * D; o.C = dst; o.ldc = D;
       o.aux_h = cur; o.ld_h = D; o.aux_z = z; o.ld_z = D;
       o.epi = EPI_GRU_OUT; o.act = activation;
       RGNN_PROPAGATE(run_gemm(o, ar, stream));
@@ -626,7 +628,7 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
   for (int t = 0; t < num_timesteps; ++t) {                                   // gnn_film.py:85
     float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
     RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));        // :94 on nodes
-    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));  // :102
+    RGNN_PROPAGATE(gemm_shared_a(ar, cur, plan->Vt, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));  // :102, target rows only
     SegParams s;
     seg_from_plan(s, plan);
     s.D = D; s.table = T; s.stride_idx = (long)L * D; s.stride_type = D;

@@ -173,6 +173,13 @@ int plan_ensure_reverse(rgnn_plan* plan, cudaStream_t stream) {
 
 using namespace rgnn;
 
+extern "C" int rgnn_plan_set_num_targets(rgnn_plan_t* plan, int32_t num_targets) {
+  RGNN_REQUIRE(plan != nullptr, "plan_set_num_targets: plan is NULL");
+  RGNN_REQUIRE(num_targets >= 0 && num_targets <= plan->V, "plan_set_num_targets: %d outside [0, V=%d]", num_targets, plan->V);
+  plan->Vt = num_targets;
+  return RGNN_OK;
+}
+
 extern "C" int rgnn_plan_create(rgnn_plan_t** out, int32_t num_nodes, int32_t num_edge_types,
                                 const int32_t* const* adjacency_lists, const int64_t* num_edges, void* stream_) {
   return rgnn_plan_create_ex(out, num_nodes, num_edge_types, adjacency_lists, num_edges, 0, stream_);
@@ -216,7 +223,8 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
     if (num_edges[l] > maxE) maxE = (int32_t)num_edges[l];
   }
   plan->type_off[num_edge_types] = (int32_t)M;
-  plan->V = num_nodes; plan->L = num_edge_types; plan->M = M; plan->max_type_edges = maxE;
+  plan->V = num_nodes;
+  plan->Vt = num_nodes; plan->L = num_edge_types; plan->M = M; plan->max_type_edges = maxE;
   cudaGetDevice(&plan->device);
 
   auto fail = [&](int code) {

@@ -4,6 +4,7 @@
 
 struct rgnn_plan {
   int32_t V = 0;
+  int32_t Vt = 0;               // rows [0, Vt) are the targets whose outputs are wanted (rgnn_plan_set_num_targets); default V
   int32_t L = 0;
   int64_t M = 0;
   // CSR by target over all edge types; incoming edges of v sorted by (type, original position)

@@ -61,6 +61,7 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_int, _PTR, _PTR, c_size_t, _PTR]),
     "rgnn_rgdcn_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, c_int, _PTR, c_int, c_int, c_int, c_int, _PTR,
                                    _PTR, c_size_t, _PTR]),
+    "rgnn_plan_set_num_targets": (c_int, [_PTR, c_int32]),
     "rgnn_segment_aggregate": (c_int, [_PTR, _PTR, c_int32, c_int, _PTR, _PTR]),
     "rgnn_edge_aggregate_forward": (c_int, [_PTR, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
     "rgnn_edge_aggregate_backward": (c_int, [_PTR, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
@@ -304,6 +305,13 @@ class GraphPlan:
             n = self.num_nodes if by == "source" else self.num_nodes * L
             return GraphPlan(lists, n, device=self.device, validate=False)
         return self._cached("plan_" + by, make)
+
+    def set_num_targets(self, num_targets: int) -> "GraphPlan":
+        """Sharded execution: only rows [0, num_targets) are wanted as outputs (owned nodes first, halo nodes after them,
+        as NodeRangePartition numbers them).  See rgnn_plan_set_num_targets in include/rgnn.h."""
+        check(load_library().rgnn_plan_set_num_targets(self.handle, int(num_targets)))
+        self.num_targets = int(num_targets)
+        return self
 
     def check(self):
         """Synchronise the creation stream and raise if the index-range check failed (deferred validation)."""

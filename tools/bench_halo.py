@@ -25,6 +25,8 @@ h_all = np.tanh(np.random.default_rng(1).standard_normal((b.num_nodes, D))).asty
 w = W.to_torch(W.film_weights(len(b.adjacency_lists), D, D), dev)
 part = NodeRangePartition(b.adjacency_lists, b.type_to_num_incoming_edges, b.num_nodes, rank, world)
 plan = G.GraphPlan(part.local_adjacency_lists, part.n_local, device=dev)
+if os.environ.get("RESTRICT_TARGETS", "1") == "1":
+    plan.set_num_targets(part.n_own)          # target-side GEMMs and the edge stage only for the owned rows
 cnt = torch.as_tensor(part.local_num_incoming).to(dev)
 h_own = torch.as_tensor(h_all[part.lo:part.hi]).to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
