@@ -190,6 +190,65 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const 
   seg_finish<NV>(p, v, col0, lane, ok, end - beg, acc);
 }
 
+// Small batches (V * D/128 warps do not fill the 148 SMs: the PPI-shaped single graph has 4,490) leave the warp-per-128-column
+// kernel latency-bound at ~40 % of the resident-warp limit (profiles/r01_final_kernels.txt).  Here a warp owns a 64-column
+// slice and its two half-warps gather two DIFFERENT edges of the target per load instruction (each 16 lanes x 16 B = 256 B),
+// so the same bytes per instruction are in flight from twice as many warps; the two partial sums are combined with one
+// xor-16 shuffle round at the end (fixed order: deterministic).  Linear messages, sum / mean / sqrt_n only.
+// Measured (B200, PPI-shaped RGCN step, cold L2): 87.84 -> 87.55 us per 3-layer step, single cold layer 34.8 -> 33.5 us --
+// i.e. occupancy was NOT the limiter; the edge stage is bound by L2 -> SM delivery.  Kept (it is never slower).
+template <bool SCALED>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_half_kernel(const __grid_constant__ SegParams p) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (v >= p.V) return;
+  const int col0 = blockIdx.y * 64 + l16 * 4;
+  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  if (p.heavy_threshold > 0 && end - beg > p.heavy_threshold) return;   // left to seg_reduce_heavy_kernel
+  const bool okc = col0 < p.D;
+  float4 acc = f4(0.0f);
+  const float* tbase = p.table + col0;
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int n = min(32, end - e0);
+    float my_scale = 1.0f;
+    long my_off = 0;
+    if (lane < n) {
+      const int ty = __ldg(p.e_type + e0 + lane);
+      const int idx = __ldg(p.e_idx + e0 + lane);
+      my_off = (long)idx * p.stride_idx + (long)ty * p.stride_type;
+      if (SCALED) my_scale = 1.0f / (__ldg(p.num_incoming + (size_t)ty * p.scale_ld + (p.scale_by_idx ? idx : v)) + 1e-7f);
+    }
+    for (int j = 0; j < n; j += 2 * UNROLL) {
+      float4 r[UNROLL];
+      bool valid[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int e = j + 2 * u + half;                 // <= 31
+        const long off = __shfl_sync(0xffffffffu, my_off, e);
+        valid[u] = okc && e < n;
+        if (valid[u]) r[u] = ldg4(tbase + off);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const float sc = SCALED ? __shfl_sync(0xffffffffu, my_scale, j + 2 * u + half) : 1.0f;
+        if (valid[u]) {
+          if (SCALED) {
+            acc.x = fmaf(r[u].x, sc, acc.x); acc.y = fmaf(r[u].y, sc, acc.y);
+            acc.z = fmaf(r[u].z, sc, acc.z); acc.w = fmaf(r[u].w, sc, acc.w);
+          } else {
+            acc = add4(acc, r[u]);
+          }
+        }
+      }
+    }
+  }
+  acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+  acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+  bool ok1[1] = {okc && half == 0};
+  float4 a1[1] = {acc};
+  seg_finish<1>(p, v, col0, lane, ok1, end - beg, a1);
+}
+
 // Degree skew: a target with thousands of incoming edges would serialise on one warp (Zipf-skewed PPI-shaped
 // batch: 1.0 ms instead of 35 us per layer).  Here a whole CTA takes one heavy target: warp w reduces the
 // 32-edge chunks w, w+8, ..., the 8 partial rows are combined in a fixed order (still deterministic).
@@ -644,7 +703,24 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
     RGNN_REQUIRE(p.stride_type == 0 || (p.stride_idx % p.stride_type) == 0, "segment reduce: stride_idx must be a multiple of stride_type");
     // one warp per 128-column slice: measured 2.2x faster than whole-row warps at D=256 (the loop is
     // latency-bound, more independent warps win: profiles/r01_seg_reduce_v3.txt)
-    if (seg_cols() == 256 && p.D > 128) launch_seg_nv<2>(p, dim3(gx, (p.D + 255) / 256), stream);
+    // small problems: twice as many warps, two edges per load instruction (seg_reduce_half_kernel)
+    static const int half_env = getenv("RGNN_SEG_HALF") ? atoi(getenv("RGNN_SEG_HALF")) : -1;   // 0 / 1 force, default auto
+    const long warps128 = (long)p.V * ((p.D + 127) / 128);
+    const bool half_ok = p.msg_mode == MSG_LINEAR && p.agg != RGNN_AGG_MAX && p.act_msg == RGNN_ACT_LINEAR && p.D >= 64;
+    const bool use_half = half_ok && (half_env == 1 || (half_env != 0 && warps128 < 148L * 40));
+    if (use_half) {
+      const dim3 grid(gx, (p.D + 63) / 64);
+      if (p.num_incoming != nullptr) seg_reduce_half_kernel<true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+      else seg_reduce_half_kernel<false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+      count_launch();
+      if (p.heavy_threshold > 0 && p.heavy_known != 0) {   // heavy targets: same split kernel as the standard path
+        const unsigned hx = p.heavy_known > 0 ? (unsigned)(p.heavy_known < 592 ? p.heavy_known : 592) : 148u;
+        const dim3 hgrid(hx, (p.D + 127) / 128);
+        if (p.num_incoming != nullptr) seg_reduce_heavy_kernel<1, MSG_LINEAR, false, true, false><<<hgrid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+        else seg_reduce_heavy_kernel<1, MSG_LINEAR, false, false, false><<<hgrid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+        count_launch();
+      }
+    } else if (seg_cols() == 256 && p.D > 128) launch_seg_nv<2>(p, dim3(gx, (p.D + 255) / 256), stream);
     else launch_seg_nv<1>(p, dim3(gx, (p.D + 127) / 128), stream);
   }
   RGNN_CHECK_CUDA(cudaGetLastError());
