@@ -151,6 +151,72 @@ __device__ __noinline__ TileInfo decode_tile(const TcParams& p, int t, int cr) {
   return ti;
 }
 
+// One warp's share of a tile's write-back: for the 32-column blocks cb = cb_begin, cb_begin + cb_step, ... read this warp's 32
+// TMEM lanes (thread = row) with tcgen05.ld, stage them in padded shared memory, and store rows so that 8 lanes write 128
+// contiguous bytes (every store instruction covers 4 full 128-byte lines).  Called from ONE site that the epilogue
+// warps (all blocks, or every third block of a CTA's last tile) and the producer warps (helping with the last tile) share.
+template <int EPI>
+__device__ __forceinline__ void epilogue_blocks(const TcParams& p, const TileInfo ti, uint32_t lane_base, uint32_t stage_q,
+                                             int quarter, int lane, int cb_begin, int cb_step) {
+  const GemmParams& g = p.g;
+  const int BN = p.BN;
+  const uint32_t srow_w = stage_q + (uint32_t)lane * EPI_PITCH;
+  const int sub_row = lane >> 3, sub_c4 = lane & 7;  // read mapping: 4 rows x 8 float4 per instruction
+  const int dgru = (EPI == EPI_GRU_ZR) ? g.N / 2 : g.N;
+  float* C = g.C + (g.batch_mode == BATCH_COL_BLOCKS ? (size_t)ti.z * g.N : 0);
+  const int n0 = ti.n_tile * BN;
+  for (int cb = cb_begin; cb < BN; cb += cb_step) {
+    {
+      float v[16];
+      tmem_ld16(lane_base + cb, v);
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd)
+        sts128(srow_w + (uint32_t)(qd * 16), make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]));
+      tmem_ld16(lane_base + cb + 16, v);
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd)
+        sts128(srow_w + (uint32_t)(64 + qd * 16), make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]));
+    }
+    __syncwarp();
+    const int c = n0 + cb + sub_c4 * 4;
+    const bool col_ok = c < p.n_total;
+    float4 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = lds128(stage_q + (uint32_t)(j * 4 + sub_row) * EPI_PITCH + (uint32_t)sub_c4 * 16);
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ti.m0 + quarter * 32 + j * 4 + sub_row;
+      if (r < ti.row_end && col_ok) {
+        float4 x = make_float4(o[j].x + bias4.x, o[j].y + bias4.y, o[j].z + bias4.z, o[j].w + bias4.w);
+        if (EPI == EPI_STORE) {
+          x = act4_cold(x, g.act);
+          *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = x;
+        } else if (EPI == EPI_GRU_ZR) {
+          x.x = hard_sigmoid(x.x); x.y = hard_sigmoid(x.y); x.z = hard_sigmoid(x.z); x.w = hard_sigmoid(x.w);
+          if (c < dgru) {
+            *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = x;                      // z gate
+          } else {
+            const int cc = c - dgru;
+            const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + cc));
+            *reinterpret_cast<float4*>(g.C2 + (size_t)r * g.ldc2 + cc) = make_float4(x.x * h.x, x.y * h.y, x.z * h.z, x.w * h.w);
+          }
+        } else {  // EPI_GRU_OUT: h' = z*h + (1-z)*act(.)
+          x = act4_cold(x, g.act);
+          const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + c));
+          const float4 zz = __ldg(reinterpret_cast<const float4*>(g.aux_z + (size_t)r * g.ld_z + c));
+          *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) =
+              make_float4(zz.x * h.x + (1.0f - zz.x) * x.x, zz.y * h.y + (1.0f - zz.y) * x.y,
+                          zz.z * h.z + (1.0f - zz.z) * x.z, zz.w * h.w + (1.0f - zz.w) * x.w);
+        }
+      }
+    }
+    __syncwarp();                               // staging rows are rewritten by the next column block
+  }
+}
+
 // CL = thread-block cluster size (1, 2 or 4).  The CL CTAs of a cluster work on CL consecutive m-tiles of the SAME
 // n-tile in lock step; each loads 1/CL of every weight-image chunk and TMA-multicasts it to all of them, so the
 // L2->SM traffic of B (the bound of this kernel, profiles/r01_gemm_tcgen05_timeline.txt) drops by CL.
@@ -304,76 +370,33 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
       }
     }
     __syncwarp();
-  } else {
-    // =========================== epilogue warps ===========================
-    // Per 32-column block: tcgen05.ld (thread = row) -> padded smem -> 8 lanes per row read 128 contiguous bytes,
-    // so every global store instruction writes 4 full 128-byte lines; all 8 stores of a block are in flight.
-    const int quarter = warp;                        // warps 0-3 own TMEM lanes [32*warp, 32*warp+32)
-    const uint32_t srow_w = estage + (uint32_t)(quarter * 32 + lane) * EPI_PITCH;
-    const int sub_row = lane >> 3, sub_c4 = lane & 7;  // read mapping: 4 rows x 8 float4 per instruction
-    const int dgru = (EPI == EPI_GRU_ZR) ? g.N / 2 : g.N;
-    for (int it = 0; it < my_tiles; ++it) {
+  }
+
+  if (warp < MMA_WARP) {
+    // =========================== write-back (epilogue warps; producer warps for the last tile) ===========================
+    // Warps 0-3 write back every tile.  Once the producer warps have nothing left to produce they help with this CTA's LAST
+    // tile: of its 32-column blocks the epilogue warps keep 0, 3, 6, ..., producer group g takes 1 + g, 4 + g, ...  A warp may
+    // only read the TMEM lanes of its quarter (warp index % 4).  When tfull has fired every MMA has consumed its operands, so
+    // the operand ring is free and serves as the helpers' staging area.  With one tile per CTA the write-back was ~37 % of
+    // the kernel (profiles/r01_gemm_tcgen05_timeline.txt).
+    const bool is_prod = warp >= PROD_WARP0;
+    const int quarter = warp & 3;
+    const int pgroup = is_prod ? (warp - PROD_WARP0) / TC_GROUP_WARPS : 0;
+    const uint32_t stage_q = is_prod ? ring + (uint32_t)((pgroup * 4 + quarter) * 32) * EPI_PITCH
+                                     : estage + (uint32_t)(quarter * 32) * EPI_PITCH;
+    const int cb_last = is_prod ? (1 + pgroup) * EPI_COLS : 0;
+    for (int it = is_prod ? my_tiles - 1 : 0; it < my_tiles; ++it) {
       const int a = it & 1;
       const TileInfo ti = decode_tile<CL>(p, cid + it * ncl, cr);
-      float* C = g.C + (g.batch_mode == BATCH_COL_BLOCKS ? (size_t)ti.z * g.N : 0);
-      const int n0 = ti.n_tile * BN;
       mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
       __syncwarp();
       tc_fence_after_sync();
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_cols);
-      for (int cb = 0; cb < BN; cb += EPI_COLS) {
-        {
-          float v[16];
-          tmem_ld16(lane_base + cb, v);
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd)
-            sts128(srow_w + (uint32_t)(qd * 16), make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]));
-          tmem_ld16(lane_base + cb + 16, v);
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd)
-            sts128(srow_w + (uint32_t)(64 + qd * 16), make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]));
-        }
-        __syncwarp();
-        const int c = n0 + cb + sub_c4 * 4;
-        const bool col_ok = c < p.n_total;
-        float4 o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = lds128(estage + (uint32_t)(quarter * 32 + j * 4 + sub_row) * EPI_PITCH + (uint32_t)sub_c4 * 16);
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = ti.m0 + quarter * 32 + j * 4 + sub_row;
-          if (r < ti.row_end && col_ok) {
-            float4 x = make_float4(o[j].x + bias4.x, o[j].y + bias4.y, o[j].z + bias4.z, o[j].w + bias4.w);
-            if (EPI == EPI_STORE) {
-              x = act4_cold(x, g.act);
-              *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = x;
-            } else if (EPI == EPI_GRU_ZR) {
-              x.x = hard_sigmoid(x.x); x.y = hard_sigmoid(x.y); x.z = hard_sigmoid(x.z); x.w = hard_sigmoid(x.w);
-              if (c < dgru) {
-                *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) = x;                      // z gate
-              } else {
-                const int cc = c - dgru;
-                const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + cc));
-                *reinterpret_cast<float4*>(g.C2 + (size_t)r * g.ldc2 + cc) = make_float4(x.x * h.x, x.y * h.y, x.z * h.z, x.w * h.w);
-              }
-            } else {  // EPI_GRU_OUT: h' = z*h + (1-z)*act(.)
-              x = act4_cold(x, g.act);
-              const float4 h = __ldg(reinterpret_cast<const float4*>(g.aux_h + (size_t)r * g.ld_h + c));
-              const float4 zz = __ldg(reinterpret_cast<const float4*>(g.aux_z + (size_t)r * g.ld_z + c));
-              *reinterpret_cast<float4*>(C + (size_t)r * g.ldc + c) =
-                  make_float4(zz.x * h.x + (1.0f - zz.x) * x.x, zz.y * h.y + (1.0f - zz.y) * x.y,
-                              zz.z * h.z + (1.0f - zz.z) * x.z, zz.w * h.w + (1.0f - zz.w) * x.w);
-            }
-          }
-        }
-        __syncwarp();                               // staging rows are rewritten by the next column block
-      }
+      const bool last = (it == my_tiles - 1);
+      epilogue_blocks<EPI>(p, ti, lane_base, stage_q, quarter, lane, last ? cb_last : 0, last ? 3 * EPI_COLS : EPI_COLS);
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * a);  // this warp's TMEM lanes of accumulator a are drained
+      if (!is_prod && lane == 0) mbar_arrive(tempty0 + 8 * a);  // this warp's TMEM lanes of accumulator a are drained
     }
   }
 
