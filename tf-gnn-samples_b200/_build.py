@@ -46,6 +46,29 @@ def is_current():
         return f.read().strip() == _source_digest()
 
 
+def build_variant(name: str, extra_flags):
+    """A second library lib/librgnn_<name>.so compiled with extra nvcc flags (e.g. -DRGNN_GEMM_TRACE for tools/gemm_trace.py).
+    Measurement tooling only: the package always loads lib/librgnn.so unless a tool points _build.LIB_PATH elsewhere."""
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found")
+    obj_dir = os.path.join(LIB_DIR, "obj_" + name)
+    os.makedirs(obj_dir, exist_ok=True)
+    out = os.path.join(LIB_DIR, "librgnn_%s.so" % name)
+    objs = []
+    for src in [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        res = subprocess.run([nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))
+        objs.append(obj)
+    res = subprocess.run([nvcc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ and link lib/librgnn.so.  Returns the library path."""
     if not force and is_current():

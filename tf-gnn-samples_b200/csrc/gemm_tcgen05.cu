@@ -36,6 +36,16 @@ constexpr int TC_PRODUCER_WARPS = TC_GROUPS * TC_GROUP_WARPS;
 constexpr int TC_GROUP_THREADS = 32 * TC_GROUP_WARPS;
 constexpr int A_IMG_BYTES = TC_BM * 128;     // 16 KB
 constexpr size_t TC_SMEM_MAX = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100
+// Per-CTA cycle trace of the kernel's phases (tools/gemm_trace.py builds a second library with -DRGNN_GEMM_TRACE; the
+// shipped library compiles these hooks away).  Slots: 0 entry, 1 set-up done, 2+q producer published chunk q, 18+q MMA saw
+// chunk q full, 34+q MMA committed chunk q, 50 accumulator complete (seen by epilogue warp 0), 51 epilogue warp 0 done,
+// 52 / 53 producer warp 4 starts / finishes helping, 54 teardown, 55 / 56 first / last weight-image copy issued.
+#ifdef RGNN_GEMM_TRACE
+__device__ long long g_gemm_trace[160 * 64];
+#define TC_TRACE(slot) do { g_gemm_trace[(blockIdx.x % 160) * 64 + (slot)] = clock64(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
 constexpr size_t TC_RING_BUDGET = TC_SMEM_MAX - 1024 /*align*/ - 18432 /*epilogue staging*/ - 512 /*barriers*/;
 
 // -------------------------------------------------------------------------------------------------
@@ -241,6 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   const uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
   const int my_tiles = (p.total_tiles - cid + ncl - 1) / ncl;   // tile groups of this cluster (same for its CTAs)
 
+  if (tid == 0) TC_TRACE(0);
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, TC_GROUP_THREADS + 1);   // one producer group + the B loader's expect_tx arrival
@@ -262,6 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   if (CL > 1) cluster_sync_all();                       // every CTA's barriers are initialised before any remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = lds32(tmem_slot);
+  if (tid == 0) TC_TRACE(1);
 
   if (warp >= PROD_WARP0 && warp < MMA_WARP) {
     // =========================== A producers ===========================
@@ -310,6 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
       }
       fence_proxy_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(full0 + 8 * s);
+      if (ptid == 0 && q < 16) TC_TRACE(2 + q);
       if (q + TC_GROUPS < total_q) load_a_chunk(q + TC_GROUPS, va);
     }
   } else if (warp == MMA_WARP) {
@@ -326,6 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
           const int s = q % S;
           mbar_wait(full0 + 8 * s, (q / S) & 1);
           tc_fence_after_sync();
+          if (q < 16) TC_TRACE(18 + q);
           const uint32_t a_hi = ring + (uint32_t)(s * stage_bytes);
           const uint32_t a_lo = a_hi + A_IMG_BYTES;
           const uint32_t b_hi = a_lo + A_IMG_BYTES;
@@ -341,6 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
           }
           if (CL > 1) umma_commit_multicast(empty0 + 8 * s, cl_mask);   // every CTA's loaders learn that this CTA is done with stage s
           else umma_commit(empty0 + 8 * s);         // stage reusable once these MMAs have read it
+          if (q < 16) TC_TRACE(34 + q);
         }
         umma_commit(tfull0 + 8 * a);                // accumulator complete -> epilogue
       }
@@ -359,6 +374,8 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
           if (use > 0) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
           const uint32_t b_hi = ring + (uint32_t)(s * stage_bytes + 2 * A_IMG_BYTES);
           mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);   // the whole chunk lands here, 1/CL from each CTA
+          if (q == 0) TC_TRACE(55);
+          TC_TRACE(56);
           if (CL > 1) {
             const uint32_t part = (uint32_t)(2 * b_img_bytes) / CL;
             bulk_copy_g2s_multicast(b_hi + cr * part, reinterpret_cast<const char*>(src_tile + (size_t)c * 2 * (BN * TC_BK)) + (size_t)cr * part,
@@ -393,7 +410,11 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
       tc_fence_after_sync();
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_cols);
       const bool last = (it == my_tiles - 1);
+      if (lane == 0 && warp == 0 && it == 0) TC_TRACE(50);
+      if (lane == 0 && warp == PROD_WARP0) TC_TRACE(52);
       epilogue_blocks<EPI>(p, ti, lane_base, stage_q, quarter, lane, last ? cb_last : 0, last ? 3 * EPI_COLS : EPI_COLS);
+      if (lane == 0 && warp == 0 && it == 0) TC_TRACE(51);
+      if (lane == 0 && warp == PROD_WARP0) TC_TRACE(53);
       tc_fence_before_sync();
       __syncwarp();
       if (!is_prod && lane == 0) mbar_arrive(tempty0 + 8 * a);  // this warp's TMEM lanes of accumulator a are drained
@@ -403,6 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
+  if (tid == 0) TC_TRACE(54);
   if (CL > 1) cluster_sync_all();                       // no CTA leaves while peers may still multicast into it / arrive on it
   if (warp == MMA_WARP) {
     tc_fence_after_sync();
@@ -634,3 +656,10 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
 }
 
 }  // namespace rgnn
+
+#ifdef RGNN_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int rgnn_debug_gemm_trace(long long* host_out, int count) {
+  if (host_out == nullptr || count <= 0 || count > 160 * 64) return -1;
+  return cudaMemcpyFromSymbol(host_out, rgnn::g_gemm_trace, sizeof(long long) * (size_t)count) == cudaSuccess ? 0 : -2;
+}
+#endif
