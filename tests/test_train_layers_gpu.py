@@ -222,3 +222,39 @@ def test_training_mode_matches_inference_kernels(cuda_device):
         composed = fn(h.clone().requires_grad_(True), *args[1:], weights=wi, **kw)
         assert composed.requires_grad
         assert rel(composed.detach().cpu().numpy(), fused.cpu().numpy()) < 2e-5, fn.__name__
+
+
+def test_empty_and_degenerate_inputs(cuda_device):
+    """No edges at all, a single node, zero rows: the differentiable building blocks and RGDCN return the reference's
+    values (sums over nothing = 0, act(0)) and zero gradients instead of faulting."""
+    import torch
+    from tf_gnn_samples_b200 import sparse_rgdcn_layer
+    empty = [np.zeros((0, 2), np.int32) for _ in range(3)]
+    Vn, Dn = 7, 16
+    plan = GraphPlan(empty, Vn, device=cuda_device)
+    assert plan.num_edges == 0
+    table = torch.randn(Vn, 3, Dn, device=cuda_device, requires_grad=True)
+    out = ops.edge_aggregate(table, plan, None, "sum")
+    assert torch.count_nonzero(out) == 0
+    out.sum().backward()
+    assert torch.count_nonzero(table.grad) == 0
+    data = torch.zeros((0, Dn), device=cuda_device, requires_grad=True)
+    assert torch.count_nonzero(ops.segment_aggregate(plan, data, "mean")) == 0
+    assert float(ops.segment_aggregate(plan, data, "max").max()) < -3e38          # tf.unsorted_segment_max of empty segments
+    x = torch.randn(Vn, Dn, device=cuda_device, requires_grad=True)
+    assert ops.gather_rows(x, plan, "source").shape == (0, Dn)
+    # dense gradients with zero rows: grad_W is exactly zero, grad_x is empty
+    gx, gw = ops.dense_backward(torch.zeros((0, 8), device=cuda_device), torch.randn(8, 12, device=cuda_device),
+                                torch.zeros((0, 12), device=cuda_device))
+    assert gx.shape == (0, 8) and torch.count_nonzero(gw) == 0
+    # RGDCN without edges: act(0) = 0 for tanh
+    w = W.to_torch(W.rgdcn_weights(3, 4, 4, stddev=0.3), cuda_device)
+    cnt = torch.zeros((3, Vn), device=cuda_device)
+    got = sparse_rgdcn_layer(torch.randn(Vn, Dn, device=cuda_device), plan, cnt, 4, 4, weights=w)
+    assert torch.count_nonzero(got) == 0
+    # one node, one self loop, training path of GGNN
+    one = GraphPlan([np.array([[0, 0]], np.int32)], 1, device=cuda_device)
+    wg = to_dev(W.ggnn_weights(1, Dn, seed=3), torch.device(cuda_device))
+    h1 = torch.randn(1, Dn, device=cuda_device, requires_grad=True)
+    sparse_ggnn_layer(h1, one, Dn, weights=wg).sum().backward()
+    assert torch.isfinite(h1.grad).all()
