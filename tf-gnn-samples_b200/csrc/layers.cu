@@ -846,7 +846,7 @@ extern "C" int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const fl
 extern "C" int rgnn_dense_backward(const float* a, int32_t m, int32_t k, const float* b, int32_t n, const float* grad_c,
                                    float* grad_a, float* grad_b, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RGNN_REQUIRE(grad_c != nullptr && m >= 0 && k > 0 && n > 0 && (k % 4) == 0 && (n % 4) == 0, "dense_backward: bad arguments (m=%d k=%d n=%d)", m, k, n);
+  RGNN_REQUIRE((grad_c != nullptr || m == 0) && m >= 0 && k > 0 && n > 0 && (k % 4) == 0 && (n % 4) == 0, "dense_backward: bad arguments (m=%d k=%d n=%d)", m, k, n);
   RGNN_REQUIRE(gemm_use_tcgen05(), "dense_backward needs the tcgen05 GEMM (unset RGNN_GEMM_IMPL=mma)");
   if (grad_a != nullptr && m > 0) {   // dA = dC . B^T
     RGNN_REQUIRE(b != nullptr, "dense_backward: grad_a needs b");

@@ -78,6 +78,8 @@ def dense(x: torch.Tensor, kernel: torch.Tensor, bias: Optional[torch.Tensor] = 
 
 def _segment_raw(plan: GraphPlan, data: torch.Tensor, agg_code: int) -> torch.Tensor:
     out = torch.empty((plan.num_nodes, data.shape[1]), dtype=torch.float32, device=data.device)
+    if data.shape[0] == 0:            # no messages: an empty tensor has no device pointer; the kernel never dereferences it
+        data = torch.zeros((1, data.shape[1]), dtype=torch.float32, device=data.device)
     with torch.cuda.device(data.device):
         check(load_library().rgnn_segment_aggregate(plan.handle, data.data_ptr(), data.shape[1], agg_code,
                                                     out.data_ptr(), current_stream_ptr(data.device)))
