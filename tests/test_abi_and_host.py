@@ -166,3 +166,33 @@ def test_qm9_full_validation_set_counts_when_the_reference_data_is_present():
     b4, _, _ = batching.qm9_batch(recs, add_self_loop_edges=False)
     assert (b5.num_graphs, b5.num_nodes, b5.num_edges, len(b5.adjacency_lists)) == (10000, 180560, 554026, 5)
     assert (b4.num_nodes, b4.num_edges, len(b4.adjacency_lists)) == (180560, 373466, 4)
+
+
+def test_ppi_fold_loader_follows_the_reference(tmp_path):
+    """tasks/ppi_task.py:68-160 on a tiny data set written in the dgl ppi.zip layout: two graphs interleaved in node-id
+    ranges [0, 4) and [4, 7), links in arbitrary order."""
+    import json
+    from tf_gnn_samples_b200 import batching
+    links = [(0, 1), (5, 4), (2, 3), (3, 0), (6, 5), (1, 1)]
+    (tmp_path / "train_graph.json").write_text(json.dumps({"links": [{"source": s, "target": t} for s, t in links]}))
+    rng = np.random.default_rng(0)
+    np.save(tmp_path / "train_feats.npy", rng.standard_normal((7, 5)).astype(np.float32))
+    np.save(tmp_path / "train_labels.npy", (rng.random((7, 3)) < 0.5).astype(np.int64))
+    np.save(tmp_path / "train_graph_id.npy", np.array([11, 11, 11, 11, 12, 12, 12]))
+    graphs, labels = batching.load_ppi_fold(str(tmp_path), "train")
+    assert len(graphs) == 2 and [g.node_features.shape[0] for g in graphs] == [4, 3] and labels[1].shape == (3, 3)
+    g0, g1 = graphs
+    assert len(g0.adjacency_lists) == 3                                       # fwd, self-loop, bkwd (:99-106)
+    assert g0.adjacency_lists[0].tolist() == [[0, 1], [2, 3], [3, 0], [1, 1]]     # file order, ids already local
+    assert g1.adjacency_lists[0].tolist() == [[1, 0], [2, 1]]                     # shifted by the graph's first node id 4
+    assert g0.adjacency_lists[1].tolist() == [[i, i] for i in range(4)]
+    assert g1.adjacency_lists[2].tolist() == [[0, 1], [1, 2]]                     # (tgt, src)
+    assert g0.type_to_node_to_num_incoming_edges.tolist() == [[1, 2, 0, 1], [1, 1, 1, 1], [1, 1, 1, 1]]
+    b = batching.pack_batch(graphs)
+    assert b.num_nodes == 7 and b.num_edges == 6 + 7 + 6
+    assert b.adjacency_lists[0].tolist()[-2:] == [[5, 4], [6, 5]]                 # second graph offset by 4 in the batch
+    tied, _ = batching.load_ppi_fold(str(tmp_path), "train", add_self_loop_edges=False, tie_fwd_bkwd_edges=True)
+    assert len(tied[0].adjacency_lists) == 1
+    import pytest
+    with pytest.raises(ValueError):
+        batching.load_ppi_fold(str(tmp_path), "dev")

@@ -91,6 +91,52 @@ def make_qm9_like_graphs(num_graphs: int, seed: int = 0, add_self_loop_edges: bo
     return [make_qm9_like_graph(rng, add_self_loop_edges=add_self_loop_edges) for _ in range(num_graphs)]
 
 
+# ---- PPI files (tasks/ppi_task.py:68-160; the dgl "ppi.zip" layout: <fold>_graph.json, _feats.npy, _labels.npy, _graph_id.npy) ----
+def load_ppi_fold(data_dir: str, fold: str = "train", add_self_loop_edges: bool = True, tie_fwd_bkwd_edges: bool = False):
+    """Read one PPI data fold the way PPI_Task.__load_data does and return (graphs, labels): one GraphSample per graph id in
+    order of first appearance, node ids shifted so every graph starts at 0 (:115-121,136-141), edge types in the reference's
+    order -- 0 = forward links in file order, then the self-loop type if enabled (one (i, i) per node, in-degree 1), then the
+    backward type (tgt, src) unless directions are tied (:99-106).  ``labels``: per graph a float32 [V_g, num_labels] array.
+    (The data set itself is not shipped with the reference; the format is the public dgl download named at :69.)"""
+    import json
+    import os
+    if fold not in ("train", "valid", "test"):
+        raise ValueError("Unknown data fold '%s'" % str(fold))
+    with open(os.path.join(data_dir, "%s_graph.json" % fold)) as f:
+        links = json.load(f)["links"]
+    feats = np.load(os.path.join(data_dir, "%s_feats.npy" % fold))
+    labels = np.load(os.path.join(data_dir, "%s_labels.npy" % fold))
+    graph_id = np.load(os.path.join(data_dir, "%s_graph_id.npy" % fold))
+    num_types = 1 + (1 if add_self_loop_edges else 0) + (0 if tie_fwd_bkwd_edges else 1)
+    self_type = 1 if add_self_loop_edges else None
+    bkwd_type = None if tie_fwd_bkwd_edges else num_types - 1
+    # graphs in order of first appearance; offset = id of the first node of the graph
+    order, first = [], {}
+    for node, g in enumerate(graph_id.tolist()):
+        if g not in first:
+            first[g] = node
+            order.append(g)
+    nodes_of = {g: np.nonzero(graph_id == g)[0] for g in order}
+    src = np.asarray([e["source"] for e in links], dtype=np.int64)
+    tgt = np.asarray([e["target"] for e in links], dtype=np.int64)
+    link_graph = graph_id[src] if len(links) else np.zeros(0, dtype=graph_id.dtype)
+    graphs, graph_labels = [], []
+    for g in order:
+        ids = nodes_of[g]
+        n, off = int(ids.shape[0]), first[g]
+        sel = link_graph == g                                   # links are assigned to the graph of their SOURCE (:137)
+        fwd = np.stack([src[sel] - off, tgt[sel] - off], axis=1).astype(np.int32).reshape(-1, 2)
+        adj = [None] * num_types
+        adj[0] = fwd
+        if self_type is not None:
+            adj[self_type] = np.stack([np.arange(n), np.arange(n)], axis=1).astype(np.int32)
+        if bkwd_type is not None:
+            adj[bkwd_type] = fwd[:, ::-1].copy()
+        graphs.append(GraphSample(adj, _in_degrees(adj, n), feats[ids].astype(np.float32)))
+        graph_labels.append(labels[ids].astype(np.float32))
+    return graphs, graph_labels
+
+
 # ---- real QM9 records (data/qm9/*.jsonl.gz of the reference; tasks/qm9_task.py:85-147) ----
 def qm9_num_edge_types(raw_graphs: Sequence[Dict], add_self_loop_edges: bool = True, tie_fwd_bkwd_edges: bool = True) -> int:
     """tasks/qm9_task.py:89-96: max bond type (+1 for the self-loop type 0), doubled when directions are untied."""
