@@ -152,6 +152,25 @@ def test_qm9_records_to_batch_follows_the_reference_loader():
     assert small.num_nodes < 100 and small.num_graphs < 200
 
 
+def test_qm9_structure_archive_reproduces_the_full_validation_batch():
+    """tests/golden/qm9_valid_structure.npz (structure of all 10,000 validation molecules) -> the BASELINE config-3 batch:
+    SURVEY.md 8d: V = 180,560, M = 373,466 (4 bond types) / 554,026 (with the self-loop type); and it agrees with the
+    200-record subset that carries real features."""
+    import os
+    from tf_gnn_samples_b200 import batching
+    here = os.path.dirname(os.path.abspath(__file__))
+    recs = batching.qm9_records_from_structure(os.path.join(here, "golden", "qm9_valid_structure.npz"))
+    assert len(recs) == 10000 and len(recs[0]["node_features"][0]) == 15
+    b4, _, _ = batching.qm9_batch(recs, add_self_loop_edges=False)
+    b5, gl, tg = batching.qm9_batch(recs)
+    assert (b4.num_nodes, b4.num_edges, len(b4.adjacency_lists)) == (180560, 373466, 4)
+    assert (b5.num_graphs, b5.num_nodes, b5.num_edges, len(b5.adjacency_lists)) == (10000, 180560, 554026, 5)
+    assert gl.shape == (180560,) and tg.shape == (1, 10000)
+    real = _qm9_subset()
+    for r_struct, r_real in zip(recs[:200], real):
+        assert r_struct["graph"] == r_real["graph"] and len(r_struct["node_features"]) == len(r_real["node_features"])
+
+
 def test_qm9_full_validation_set_counts_when_the_reference_data_is_present():
     """10,000 graphs, V = 180,560, M = 373,466 (L=4) / 554,026 (L=5).  Only runs where
     /root/reference exists (the build container)."""

@@ -191,6 +191,23 @@ def load_qm9_jsonl(path: str, limit: Optional[int] = None) -> List[Dict]:
     return out
 
 
+def qm9_records_from_structure(path: str, feature_dim: int = 15, seed: int = 0, num_targets: int = 13) -> List[Dict]:
+    """Records in the layout of data/qm9/*.jsonl.gz rebuilt from a structure-only archive (tests/golden/make_qm9_structure.py:
+    atoms per molecule + bonds of the reference's 10,000 validation molecules).  The graph structure is the real one; node
+    features are seeded random numbers and targets are zero -- for timing the real batch shape, not for accuracy work."""
+    z = np.load(path)
+    sizes, nbonds, bonds = z["num_atoms"].astype(np.int64), z["num_bonds"].astype(np.int64), z["bonds"].astype(np.int64)
+    rng = np.random.default_rng(seed)
+    recs, b0 = [], 0
+    for i in range(sizes.shape[0]):
+        n, nb = int(sizes[i]), int(nbonds[i])
+        recs.append({"id": "qm9-structure:%d" % i, "graph": bonds[b0:b0 + nb].tolist(),
+                     "node_features": rng.standard_normal((n, feature_dim)).astype(np.float32),
+                     "targets": [[0.0]] * num_targets})
+        b0 += nb
+    return recs
+
+
 def qm9_batch(raw_graphs: Sequence[Dict], add_self_loop_edges: bool = True, tie_fwd_bkwd_edges: bool = True,
               task_ids: Sequence[int] = (0,), max_nodes_per_batch: Optional[int] = None):
     """Records -> (Batch, graph_nodes_list int32 [V], target_values float32 [len(task_ids), G]): the feed_dict of
