@@ -140,3 +140,62 @@ def test_data_parallel_gradient_sync_world2():
         assert v_total == v_full
         assert err < 1e-12, "rank %d: summed shard gradients differ from the union-batch gradient: %g" % (rank, err)
         assert unused_grad == 0.0
+
+
+def _halo_train_worker(rank, world, port, ret):
+    """Training ONE graph over a node-range partition: forward halo exchange, layer on the rank-local graph, backward through
+    the transposed exchange (halo-row gradients return to their owners and are summed), weight gradients all-reduced.
+    Everything must equal single-process autograd on the whole graph.  Layer arithmetic: the float64 autograd oracle."""
+    from oracle import ref_autograd as A
+    from tf_gnn_samples_b200.scaffold import all_reduce_gradients_
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = batching.varmisuse_like_batch(num_nodes=300, num_edges=4000, seed=9, feature_dim=8)     # one random graph
+        D, Ltypes = 8, len(b.adjacency_lists)
+        h = np.tanh(np.random.default_rng(2).standard_normal((b.num_nodes, D)))
+        proj = np.random.default_rng(3).standard_normal((b.num_nodes, D))
+        w_np = W.film_weights(Ltypes, D, D, seed=4, random_ln=True)
+
+        def two_layers(states, adj, cnt, weights, exchange=None, n_own=None):
+            cur = states
+            for _ in range(2):                                           # same weights twice: gradients accumulate
+                local = exchange(cur) if exchange is not None else cur
+                out = A.sparse_gnn_film_layer(local, adj, cnt, activation_function="tanh", normalize_by_num_incoming=True, weights=weights)
+                cur = out[:n_own] if n_own is not None else out
+            return cur
+
+        # single process, whole graph
+        h_ref = torch.as_tensor(h).requires_grad_(True)
+        w_ref = A.to_torch64(w_np)
+        (two_layers(h_ref, b.adjacency_lists, torch.as_tensor(b.type_to_num_incoming_edges, dtype=torch.float64), w_ref) * torch.as_tensor(proj)).sum().backward()
+        # this rank's share
+        part = NodeRangePartition(b.adjacency_lists, b.type_to_num_incoming_edges, b.num_nodes, rank, world)
+        h_own = torch.as_tensor(h[part.lo:part.hi]).requires_grad_(True)
+        w_loc = A.to_torch64(w_np)
+        out = two_layers(h_own, part.local_adjacency_lists, torch.as_tensor(part.local_num_incoming, dtype=torch.float64), w_loc,
+                         exchange=part.exchange, n_own=part.n_own)
+        (out * torch.as_tensor(proj[part.lo:part.hi])).sum().backward()
+        params = list(A.flatten(w_loc).values())
+        all_reduce_gradients_(params)
+        err_h = float((h_own.grad - h_ref.grad[part.lo:part.hi]).abs().max() / h_ref.grad.abs().max())
+        err_w = max(float((p.grad - q.grad).abs().max() / max(float(q.grad.abs().max()), 1e-30))
+                    for p, q in zip(params, A.flatten(w_ref).values()))
+        ret[rank] = (err_h, err_w, part.n_halo)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_training_through_the_halo_exchange_world2():
+    world, port = 2, free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_halo_train_worker, args=(world, port, ret), nprocs=world, join=True)
+        res = dict(ret)
+    assert set(res) == {0, 1}
+    for rank, (err_h, err_w, n_halo) in res.items():
+        assert n_halo > 0
+        assert err_h < 1e-10, "rank %d: d/d node states through the halo exchange differs: %g" % (rank, err_h)
+        assert err_w < 1e-10, "rank %d: all-reduced weight gradients differ: %g" % (rank, err_w)

@@ -56,6 +56,37 @@ def split_batch_by_graphs(batch: Batch, parts: int) -> List[Batch]:
     return shards
 
 
+def _make_halo_exchange():
+    import torch
+
+    class HaloExchange(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, h_own, part, group):
+            ctx.part, ctx.group = part, group
+            return torch.cat([h_own, part._exchange_rows(h_own, group)], dim=0)
+
+        @staticmethod
+        def backward(ctx, g_local):
+            part = ctx.part
+            g_own = g_local[:part.n_own] + part._return_rows(g_local[part.n_own:], ctx.group)
+            return g_own, None, None
+    return HaloExchange
+
+
+class _LazyHaloExchange:
+    """torch is imported lazily in this module (the index construction is numpy-only)."""
+    _cls = None
+
+    @classmethod
+    def apply(cls, *args):
+        if cls._cls is None:
+            cls._cls = _make_halo_exchange()
+        return cls._cls.apply(*args)
+
+
+_HaloExchange = _LazyHaloExchange
+
+
 class NodeRangePartition:
     """Rank-local view of a node-range partition (targets owned, halo sources fetched).
 
@@ -120,25 +151,54 @@ class NodeRangePartition:
         self.send_counts = np.array([x.shape[0] for x in self.send_local_idx], dtype=np.int64)
         self._idx_cache = {}
 
-    def exchange(self, h_own, group=None):
-        """[n_own, D] owned states -> [n_local, D] = owned rows followed by the halo rows, via one
-        all-to-all-v (torch.distributed.all_to_all_single with uneven splits)."""
+    def _send_index(self, device):
         import torch
-        import torch.distributed as dist
-        assert h_own.shape[0] == self.n_own
-        D = h_own.shape[1]
-        key = str(h_own.device)
+        key = str(device)
         idx = self._idx_cache.get(key)
         if idx is None:   # index list is fixed per batch: build it on the device once
             idx = torch.as_tensor(np.concatenate(self.send_local_idx) if self.send_counts.sum() else np.zeros(0, np.int64),
-                                  device=h_own.device)
+                                  device=device)
             self._idx_cache[key] = idx
+        return idx
+
+    def _exchange_rows(self, h_own, group=None):
+        """[n_own, D] owned rows -> [n_halo, D] halo rows (one all-to-all-v)."""
+        import torch.distributed as dist
+        D = h_own.shape[1]
+        idx = self._send_index(h_own.device)
         send = h_own.index_select(0, idx) if idx.numel() else h_own.new_zeros((0, D))
         recv = h_own.new_empty((self.n_halo, D))
         if self.world_size > 1:
             dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=[int(x) for x in self.recv_counts],
                                    input_split_sizes=[int(x) for x in self.send_counts], group=group)
-        return torch.cat([h_own, recv], dim=0)
+        return recv
+
+    def _return_rows(self, g_halo, group=None):
+        """The transpose of ``_exchange_rows``: gradients of the halo rows travel back to their owners (the same
+        all-to-all-v with the split sizes swapped) and are ADDED to the owners' rows (a node can be in several peers' halos)."""
+        import torch
+        import torch.distributed as dist
+        D = g_halo.shape[1]
+        back = g_halo.new_empty((int(self.send_counts.sum()), D))
+        if self.world_size > 1:
+            dist.all_to_all_single(back, g_halo.contiguous(), output_split_sizes=[int(x) for x in self.send_counts],
+                                   input_split_sizes=[int(x) for x in self.recv_counts], group=group)
+        g_own = torch.zeros((self.n_own, D), dtype=g_halo.dtype, device=g_halo.device)
+        idx = self._send_index(g_halo.device)
+        if idx.numel():
+            g_own.index_add_(0, idx, back)
+        return g_own
+
+    def exchange(self, h_own, group=None):
+        """[n_own, D] owned states -> [n_local, D] = owned rows followed by the halo rows, via one
+        all-to-all-v (torch.distributed.all_to_all_single with uneven splits).  Differentiable: under autograd the
+        backward sends the halo rows' gradients back to their owners with the transposed exchange, so a layer
+        stack over a node-range partition can be trained (weights: scaffold.all_reduce_gradients_)."""
+        import torch
+        assert h_own.shape[0] == self.n_own
+        if torch.is_grad_enabled() and h_own.requires_grad:
+            return _HaloExchange.apply(h_own, self, group)
+        return torch.cat([h_own, self._exchange_rows(h_own, group)], dim=0)
 
     def halo_bytes(self, D: int) -> int:
         """Bytes this rank receives per layer (fp32 rows of width D)."""
