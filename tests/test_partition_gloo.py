@@ -199,3 +199,43 @@ def test_training_through_the_halo_exchange_world2():
         assert n_halo > 0
         assert err_h < 1e-10, "rank %d: d/d node states through the halo exchange differs: %g" % (rank, err_h)
         assert err_w < 1e-10, "rank %d: all-reduced weight gradients differ: %g" % (rank, err_w)
+
+
+def _no_halo_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # two equal graphs packed block-diagonally: the degree-balanced cut falls on the graph boundary -> no halo anywhere
+        g = batching.make_typed_random_graph(40, 300, (0.5, 0.5), 4, seed=1)
+        b = batching.pack_batch([g, g])
+        part = NodeRangePartition(b.adjacency_lists, b.type_to_num_incoming_edges, b.num_nodes, rank, world)
+        calls = {"n": 0}
+        real = dist.all_to_all_single
+
+        def counting(*a, **k):
+            calls["n"] += 1
+            return real(*a, **k)
+        dist.all_to_all_single = counting
+        try:
+            h_own = torch.randn(part.n_own, 4, dtype=torch.float64, requires_grad=True)
+            local = part.exchange(h_own)
+            local.sum().backward()
+        finally:
+            dist.all_to_all_single = real
+        ret[rank] = (part.n_halo, part.any_halo(), calls["n"], tuple(local.shape), float(h_own.grad.min()), (part.lo, part.hi))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_exchange_skips_the_collective_when_no_rank_has_a_halo_world2():
+    world, port = 2, free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_no_halo_worker, args=(world, port, ret), nprocs=world, join=True)
+        res = dict(ret)
+    for rank, (n_halo, any_halo, calls, shape, gmin, rng) in res.items():
+        assert rng in ((0, 40), (40, 80)), rng
+        assert n_halo == 0 and any_halo is False and calls == 0
+        assert shape == (40, 4) and gmin == 1.0
