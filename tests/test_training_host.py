@@ -88,3 +88,33 @@ def test_train_loop_logs_saves_best_and_stops_after_patience():
     assert lines[-2] == "Stopping training after 3 epochs without improvement on validation loss."
     assert lines[-1].startswith("Training took ") and lines[-1].endswith("Best validation results: Avg MicroF1: 0.750")
     assert model.mode == "eval" and model.eval_calls == 5
+
+
+def test_prefetch_keeps_order_bounds_the_queue_and_propagates_errors():
+    import threading
+    import time
+    produced, lock = [], threading.Lock()
+
+    def fn(i):
+        with lock:
+            produced.append(i)
+        return i * i
+
+    it = training.prefetch(range(50), fn, max_queue_size=3)
+    first = next(it)
+    time.sleep(0.2)                                                # the worker runs ahead, but only by the queue size (+1 in flight)
+    with lock:
+        ahead = len(produced)
+    assert first == 0 and 1 <= ahead <= 1 + 3 + 1
+    assert [first] + list(it) == [i * i for i in range(50)]
+
+    def bad(i):
+        if i == 3:
+            raise KeyError("boom")
+        return i
+    got = []
+    with pytest.raises(KeyError):
+        for v in training.prefetch(range(10), bad):
+            got.append(v)
+    assert got == [0, 1, 2]
+    assert list(training.prefetch([], fn)) == []

@@ -40,6 +40,35 @@ def device_args(tb: TaskBatch, device) -> Tuple:
     return args
 
 
+def prefetch(items: Iterable, fn: Callable[[Any], Any] = lambda x: x, max_queue_size: int = 5) -> Iterable:
+    """dpu_utils ThreadedIterator as the reference uses it (models/sparse_graph_model.py:270-272, queue of 5): a background
+    thread applies ``fn`` (batch construction, host->device copies, GraphPlan build) to the items in order while the
+    consumer works on earlier ones.  Exceptions raised by ``fn`` or the source iterator surface in the consumer."""
+    import queue
+    import threading
+    q: "queue.Queue" = queue.Queue(maxsize=max(1, int(max_queue_size)))
+    done = object()
+
+    def worker():
+        try:
+            for it in items:
+                q.put((True, fn(it)))
+            q.put((True, done))
+        except BaseException as exc:                   # hand the failure to the consumer instead of dying silently
+            q.put((False, exc))
+
+    t = threading.Thread(target=worker, daemon=True)
+    t.start()
+    while True:
+        ok, value = q.get()
+        if not ok:
+            raise value
+        if value is done:
+            break
+        yield value
+    t.join()
+
+
 def pretty_print_epoch_task_metrics(task: str, task_metric_results: List[Dict[str, float]], num_graphs: int,
                                     task_ids: Sequence[int] = (0,)) -> str:
     if task.lower() == "ppi":                                                   # tasks/ppi_task.py:262-264
