@@ -215,3 +215,26 @@ def test_ppi_fold_loader_follows_the_reference(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         batching.load_ppi_fold(str(tmp_path), "dev")
+
+
+def test_header_is_plain_c_and_the_c_host_example_links():
+    """include/rgnn.h must be consumable from C (the drop-in boundary is a C ABI, no C++ / torch types): compile the C99
+    example against it with warnings on, and link it against the built library when the CUDA runtime library is present."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = os.path.join(ROOT, "examples", "c_abi_demo.c")
+    with tempfile.TemporaryDirectory() as tmp:
+        obj = os.path.join(tmp, "demo.o")
+        res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj],
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        cudart = "/usr/local/cuda/lib64"
+        if os.path.exists(os.path.join(cudart, "libcudart.so")):
+            lib_dir = os.path.dirname(_build.build())
+            res = subprocess.run([gcc, obj, "-o", os.path.join(tmp, "demo"), "-L", lib_dir, "-lrgnn", "-L", cudart, "-lcudart",
+                                  "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+            assert res.returncode == 0, res.stderr
