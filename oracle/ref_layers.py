@@ -1,6 +1,12 @@
 """numpy restatement of the reference GNN layers (TEST INFRASTRUCTURE -- see oracle/__init__.py).
 
-PARITY UNPINNED (no reference tests / golden vectors exist; TF1 not installable here).
+PINNED AGAINST THE REFERENCE'S OWN CODE: the reference has no tests or golden vectors and TF1 is not installable here, but
+its layer functions are plain Python over ~25 tf.* calls, so tests/golden/make_ref_fixtures.py EXECUTES the unmodified
+/root/reference/gnns/*.py + utils/utils.py through a numpy-backed ``tensorflow`` / ``dpu_utils`` stand-in (tests/tf1_shim)
+and commits the outputs as tests/golden/ref_*.npz; tests/test_reference_pin.py holds this oracle to them at 1e-12
+(17 small cases covering every keyword argument that changes the op order, and BASELINE.json configs 2-5 at full size).
+What remains an assumption is only the TF 1.13 / Keras / dpu_utils KERNEL semantics the stand-in restates (SURVEY.md
+Appendix A); tests/golden/make_tf1_fixtures.py discharges it on a machine with the real stack.
 
 Every function follows the reference op order literally (gather -> per-edge
 transform -> scale -> concat -> unsorted segment reduce -> activation), so that

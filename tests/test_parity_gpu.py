@@ -8,7 +8,7 @@ from tf_gnn_samples_b200 import (GraphPlan, RgnnError, batching, weights as W, s
                                  sparse_gnn_edge_mlp_layer, sparse_gnn_film_layer, sparse_rgat_layer,
                                  sparse_rgcn_layer, sparse_rgin_layer)
 
-from helpers import assert_parity, node_states, tiny_graph, to_cuda_inputs
+from helpers import assert_parity, assert_parity_8c, node_states, tiny_graph, to_cuda_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -28,6 +28,11 @@ def run(layer, ref, h, adj, indeg, device, w, with_indeg, **kw):
         want = ref(h, adj, **kw, weights=w)
     torch.cuda.synchronize()
     return got.cpu().numpy(), want
+
+
+def oracle32(ref, h, adj, indeg, w, with_indeg, **kw):
+    """The reference op order in float32 (the stand-in for the TF1 CPU arithmetic): yardstick of SURVEY.md 8(c)."""
+    return ref(h, adj, indeg, **kw, weights=w, dtype=np.float32) if with_indeg else ref(h, adj, **kw, weights=w, dtype=np.float32)
 
 
 # ---------------------------------------------------------------- plan ---------------------------------
@@ -195,10 +200,11 @@ def test_film(cuda_device, normalize, agg, act, T):
     D = 128
     h = node_states(83, D)
     w = W.film_weights(5, D, D, num_timesteps=T, random_ln=True)
-    got, want = run(sparse_gnn_film_layer, R.sparse_gnn_film_layer, h, adj, indeg, cuda_device, w, True,
-                    state_dim=D, num_timesteps=T, activation_function=act, message_aggregation_function=agg,
-                    normalize_by_num_incoming=normalize)
-    assert_parity(got, want, "film norm=%s %s %s T=%d" % (normalize, agg, act, T), tol=2e-4 if T > 1 else 1e-4)
+    kw = dict(state_dim=D, num_timesteps=T, activation_function=act, message_aggregation_function=agg,
+              normalize_by_num_incoming=normalize)
+    got, want = run(sparse_gnn_film_layer, R.sparse_gnn_film_layer, h, adj, indeg, cuda_device, w, True, **kw)
+    assert_parity_8c(got, want, oracle32(R.sparse_gnn_film_layer, h, adj, indeg, w, True, **kw),
+                     "film norm=%s %s %s T=%d" % (normalize, agg, act, T))
 
 
 # ---------------------------------------------------------------- Edge-MLP -----------------------------
@@ -210,11 +216,11 @@ def test_edge_mlp(cuda_device, hidden, use_target, normalize, T):
     h = node_states(67, D)
     w = W.edge_mlp_weights(4, D, D, num_edge_hidden_layers=hidden, use_target_state_as_input=use_target,
                            num_timesteps=T, random_ln=True)
-    got, want = run(sparse_gnn_edge_mlp_layer, R.sparse_gnn_edge_mlp_layer, h, adj, indeg, cuda_device, w, True,
-                    state_dim=D, num_timesteps=T, activation_function="gelu", normalize_by_num_incoming=normalize,
-                    use_target_state_as_input=use_target, num_edge_hidden_layers=hidden)
-    assert_parity(got, want, "edge-mlp h=%d tgt=%s norm=%s T=%d" % (hidden, use_target, normalize, T),
-                  tol=2e-4 if T > 1 else 1e-4)
+    kw = dict(state_dim=D, num_timesteps=T, activation_function="gelu", normalize_by_num_incoming=normalize,
+              use_target_state_as_input=use_target, num_edge_hidden_layers=hidden)
+    got, want = run(sparse_gnn_edge_mlp_layer, R.sparse_gnn_edge_mlp_layer, h, adj, indeg, cuda_device, w, True, **kw)
+    assert_parity_8c(got, want, oracle32(R.sparse_gnn_edge_mlp_layer, h, adj, indeg, w, True, **kw),
+                     "edge-mlp h=%d tgt=%s norm=%s T=%d" % (hidden, use_target, normalize, T))
 
 
 # ---------------------------------------------------------------- RGIN ---------------------------------
@@ -227,11 +233,11 @@ def test_rgin(cuda_device, edge_h, aggr_h, use_target, T):
     h = node_states(59, D)
     w = W.rgin_weights(3, D, D, num_edge_MLP_hidden_layers=edge_h, num_aggr_MLP_hidden_layers=aggr_h,
                        use_target_state_as_input=use_target, num_timesteps=T, random_ln=True)
-    got, want = run(sparse_rgin_layer, R.sparse_rgin_layer, h, adj, None, cuda_device, w, False, state_dim=D,
-                    num_timesteps=T, activation_function="ReLU", use_target_state_as_input=use_target,
-                    num_edge_MLP_hidden_layers=edge_h, num_aggr_MLP_hidden_layers=aggr_h)
-    assert_parity(got, want, "rgin edge=%s aggr=%s tgt=%s T=%d" % (edge_h, aggr_h, use_target, T),
-                  tol=2e-4 if T > 1 else 1e-4)
+    kw = dict(state_dim=D, num_timesteps=T, activation_function="ReLU", use_target_state_as_input=use_target,
+              num_edge_MLP_hidden_layers=edge_h, num_aggr_MLP_hidden_layers=aggr_h)
+    got, want = run(sparse_rgin_layer, R.sparse_rgin_layer, h, adj, None, cuda_device, w, False, **kw)
+    assert_parity_8c(got, want, oracle32(R.sparse_rgin_layer, h, adj, None, w, False, **kw),
+                     "rgin edge=%s aggr=%s tgt=%s T=%d" % (edge_h, aggr_h, use_target, T))
 
 
 # ---------------------------------------------------------------- errors --------------------------------

@@ -224,8 +224,6 @@ def test_training_mode_matches_inference_kernels(cuda_device):
         assert rel(composed.detach().cpu().numpy(), fused.cpu().numpy()) < 2e-5, fn.__name__
 
 
-@pytest.mark.skip(reason="added after this round's GPU budget was spent: not yet run on a B200 (the code paths it covers are "
-                         "the zero-row branches of ops._segment_raw and rgnn_dense_backward); enable and run it first thing next round")
 def test_empty_and_degenerate_inputs(cuda_device):
     """No edges at all, a single node, zero rows: the differentiable building blocks and RGDCN return the reference's
     values (sums over nothing = 0, act(0)) and zero gradients instead of faulting."""
