@@ -6,13 +6,15 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product package
 of ``bench.py`` -- always as the checker / the CPU arm, never as the thing that
 is shipped.
 
-PARITY UNPINNED: the reference (microsoft/tf-gnn-samples) has no tests, golden
-vectors or fixtures, and its arithmetic lives in TensorFlow 1.13 / dpu_utils
-which cannot be installed in this image (no network, Python 3.12).  This oracle
-is an op-for-op numpy restatement of ``gnns/*.py`` + ``utils/utils.py`` written
-from the line-cited reference sources and the documented TF/Keras defaults
-(SURVEY.md Appendix A).  The only reference-owned pin available is structural
-(README.md:29 parameter count 699,257 -- see tests/test_oracle_known_answers.py).
+PINNED AGAINST THE REFERENCE'S OWN CODE (round 2): the reference (microsoft/tf-gnn-samples) has no tests, golden
+vectors or fixtures, and its arithmetic lives in TensorFlow 1.13 / dpu_utils which cannot be installed in this image (no
+network, Python 3.12) -- but ``gnns/*.py`` and ``utils/utils.py`` are plain Python over ~25 ``tf.*`` calls, so
+``tests/golden/make_ref_fixtures.py`` imports them UNMODIFIED with a numpy-backed ``tensorflow`` / ``dpu_utils`` stand-in
+(``tests/tf1_shim``), feeds them seeded inputs and weights, and commits what they return as ``tests/golden/ref_*.npz``.
+``tests/test_reference_pin.py`` holds this oracle to those files at 1e-12 (float64) for 17 small cases and for BASELINE.json
+configs 2-5 at full size.  Remaining assumption: the TF 1.13 / Keras / dpu_utils kernel semantics restated by the stand-in
+(SURVEY.md Appendix A); ``tests/golden/make_tf1_fixtures.py`` checks them against a real TensorFlow 1.13 where one exists.
+The structural known answer (README.md:29 parameter count 699,257) stays in tests/test_oracle_known_answers.py.
 
 Modules:
   ref_layers  numpy restatement (dtype-parametric: float64 "truth", float32
