@@ -41,10 +41,12 @@ extern "C" {
 #define RGNN_API
 #endif
 
-#define RGNN_VERSION 100          /* 0.1.0 */
+#define RGNN_VERSION 200          /* 0.2.0 */
 #define RGNN_MAX_EDGE_TYPES 64
 #define RGNN_MAX_MLP_LAYERS 8
 #define RGNN_MAX_STATE_DIM 512    /* per-row register tile of the segment kernels */
+#define RGNN_MAX_WORLD 16         /* ranks of one node-range partition (one NVSwitch domain) */
+#define RGNN_PEER_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 /* error codes */
 #define RGNN_OK 0
@@ -69,6 +71,7 @@ enum rgnn_layer_kind {
 };
 
 typedef struct rgnn_plan rgnn_plan_t;
+typedef struct rgnn_halo_plan rgnn_halo_plan_t;
 
 RGNN_API int rgnn_version(void);
 RGNN_API const char* rgnn_last_error(void);
@@ -216,6 +219,51 @@ RGNN_API int rgnn_rgdcn_forward(const rgnn_plan_t* plan, const float* h, int32_t
                        int activation, int aggregation, int normalize, int num_timesteps, float* out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- one large graph over several GPUs: node-range partition + halo exchange --------------------------
+ * The reference is single-device; this is the multi-GPU form of ITS batch (tasks/varmisuse_task.py:451-538 packs up to
+ * 100k nodes per batch): rank r of `world` owns the nodes [cuts[r], cuts[r+1]) and every edge whose TARGET it owns, so the
+ * segment reductions / softmax / layer norm / GRU of every layer stay local; before each layer the states of the remote
+ * SOURCE nodes ("halo") are refreshed.  One process per GPU; weights are replicated.
+ *
+ * rgnn_halo_plan_create: adjacency_lists hold GLOBAL node ids (device, int32 [E_l, 2]); edges whose target another rank
+ * owns are dropped, so every rank may pass the same lists or only its own shard.  Built on the device (order-preserving
+ * select, radix sort + unique of the remote sources, renumbering).  Local numbering: owned node g -> g - cuts[rank];
+ * halo nodes follow, sorted by global id (hence grouped by owner).  rgnn_halo_plan_graph() is the ordinary plan over the
+ * local ids with num_targets = the owned rows: pass it to any rgnn_<x>_forward with node states [n_own + n_halo, d]
+ * (num_timesteps = 1 per call; call rgnn_halo_exchange between steps).  Synchronises the stream (it sizes buffers). */
+RGNN_API int rgnn_halo_plan_create(rgnn_halo_plan_t** out, int32_t rank, int32_t world, const int64_t* cuts /* host [world+1] */,
+                          int32_t num_edge_types, const int32_t* const* adjacency_lists, const int64_t* num_edges,
+                          void* stream);
+RGNN_API int rgnn_halo_plan_destroy(rgnn_halo_plan_t* plan);
+RGNN_API int32_t rgnn_halo_plan_num_own(const rgnn_halo_plan_t* plan);
+RGNN_API int32_t rgnn_halo_plan_num_halo(const rgnn_halo_plan_t* plan);
+RGNN_API int64_t rgnn_halo_plan_num_edges(const rgnn_halo_plan_t* plan, int32_t edge_type);   /* kept edges of one type */
+RGNN_API rgnn_plan_t* rgnn_halo_plan_graph(rgnn_halo_plan_t* plan);                            /* owned by the halo plan */
+/* Copies into caller DEVICE buffers (any may be NULL): halo_global / halo_owner / halo_row [n_halo] (global id, owning rank,
+ * row inside the owner's state buffer) and the renumbered adjacency lists (host array of L device pointers, [E_l, 2]). */
+RGNN_API int rgnn_halo_plan_export(const rgnn_halo_plan_t* plan, int32_t* halo_global, int32_t* halo_owner, int32_t* halo_row,
+                          int32_t* const* local_adjacency_lists, void* stream);
+/* Peer memory.  Every rank keeps TWO state buffers (layer t reads buffer t % 2 and writes its owned rows into the other
+ * one) of [n_own + n_halo, d] floats, owned rows first, plus one flag array uint32[world], in memory that the other ranks
+ * have mapped into their address space (rgnn_peer_* below, or any other mechanism: these are plain device pointers).
+ * peer_states0/1 and peer_flags are host arrays of `world` device pointers valid IN THIS PROCESS; entry [rank] is this
+ * rank's own memory.  The flag arrays must start zeroed. */
+RGNN_API int rgnn_halo_plan_attach(rgnn_halo_plan_t* plan, void* const* peer_states0, void* const* peer_states1,
+                          void* const* peer_flags);
+/* Refresh rows [n_own, n_own + n_halo) of this rank's state buffer `buffer` with the owners' current rows, read straight
+ * out of the owners' buffers over NVLink (one kernel, pull-based: no packing, no send side).  Collective: every rank calls
+ * it the same number of times, in the same order; the kernel contains the cross-rank barrier ("every rank's owned rows of
+ * this buffer are final") as system-scope flags, and keeps its epoch on the device, so a captured CUDA graph can be
+ * replayed.  A peer that never arrives faults the kernel after 10 s instead of hanging the GPU. */
+RGNN_API int rgnn_halo_exchange(rgnn_halo_plan_t* plan, int buffer, int32_t d, void* stream);
+
+/* CUDA-IPC plumbing for the above (one node): allocate zeroed device memory that peers can map, export its 64-byte handle
+ * (ship it with any host-side channel, e.g. torch.distributed.all_gather_object), map a peer's allocation. */
+RGNN_API int rgnn_peer_alloc(void** ptr, size_t bytes, void* handle_out /* RGNN_PEER_HANDLE_BYTES */);
+RGNN_API int rgnn_peer_open(const void* handle, void** ptr);
+RGNN_API int rgnn_peer_close(void* ptr);
+RGNN_API int rgnn_peer_free(void* ptr);
+
 /* ---- building blocks exported for tests / other hosts ---------------------------------------
  * utils/utils.py:23-33: aggregate `data` [M, d] (rows in the ORIGINAL type-major message order)
  * to [V, d] with the plan's segments -- the tf.unsorted_segment_<agg> call of rgcn.py:110. */
@@ -231,14 +279,17 @@ RGNN_API int rgnn_edge_aggregate_forward(const rgnn_plan_t* plan, const float* t
 RGNN_API int rgnn_edge_aggregate_backward(const rgnn_plan_t* plan, const float* grad_out, int32_t d,
                                  const float* num_incoming, int aggregation, float* d_table, void* stream);
 /* C[M,N] = act(A[M,K] . B[K,N] + bias) on the tensor cores with 3xTF32 split accumulation
- * (fp32-accurate); the node-level Dense of every layer (A.1). bias may be NULL. */
+ * (fp32-accurate); the node-level Dense of every layer (A.1). bias may be NULL.  workspace: caller scratch of at least
+ * rgnn_dense_workspace_bytes(m, k, n) bytes (weight images; split-K partial tiles of the backward) -- the library
+ * allocates nothing per call. */
+RGNN_API size_t rgnn_dense_workspace_bytes(int32_t m, int32_t k, int32_t n);
 RGNN_API int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const float* b, int32_t n,
-                       const float* bias, int activation, float* c, void* stream);
+                       const float* bias, int activation, float* c, void* workspace, size_t workspace_bytes, void* stream);
 /* Gradients of the linear map C = A . B: grad_a [M,K] = grad_c . B^T, grad_b [K,N] = A^T . grad_c (split-K on the tensor
  * cores, deterministic).  Either output may be NULL.  The reference gets these from TF autodiff of its Dense kernels
  * (models/sparse_graph_model.py:253-260). */
 RGNN_API int rgnn_dense_backward(const float* a, int32_t m, int32_t k, const float* b, int32_t n, const float* grad_c,
-                        float* grad_a, float* grad_b, void* stream);
+                        float* grad_a, float* grad_b, void* workspace, size_t workspace_bytes, void* stream);
 /* tf.contrib.layers.layer_norm over the last axis, eps 1e-12 (A.5). */
 RGNN_API int rgnn_layer_norm(const float* x, int32_t rows, int32_t d, const float* gamma, const float* beta,
                     float* out, void* stream);

@@ -157,12 +157,16 @@ def summarize(out64):
 
 
 def compare_with_summary(got, z, what=""):
-    """max-norm relative errors of a full [V, D] result against a committed big-case summary (rows, projection, column sums);
-    the projection touches every element with weights ~N(0,1), so its error bound scales with sqrt(D)."""
+    """Errors of a full [V, D] result against a committed big-case summary, each normalised so that an element-wise max-norm
+    relative error of eps implies a value <= eps: the committed rows directly; the projection by maxabs * sum|r| and the
+    column sums by maxabs * V (|sum_j e_j r_j| <= max|e| * sum|r_j|; a sum of V errors is at most V * max|e|).  The rows
+    bound the error itself, the two sums make sure NO row outside the committed sample is badly off (an outlier of size x in
+    an uncommitted row moves the projection by ~x)."""
     got = np.asarray(got, np.float64)
     assert tuple(got.shape) == tuple(int(x) for x in z["shape"]), "%s: shape %s vs %s" % (what, got.shape, z["shape"])
     scale = float(z["maxabs"])
+    r = projection_vector(got.shape[1])
     err_rows = float(np.abs(got[::BIG_ROW_STRIDE] - z["out_rows"]).max() / scale)
-    err_proj = float(np.abs(got @ projection_vector(got.shape[1]) - z["proj"]).max() / (scale * np.sqrt(got.shape[1])))
-    err_col = float(np.abs(got.sum(axis=0) - z["colsum"]).max() / (scale * np.sqrt(got.shape[0])))
+    err_proj = float(np.abs(got @ r - z["proj"]).max() / (scale * np.abs(r).sum()))
+    err_col = float(np.abs(got.sum(axis=0) - z["colsum"]).max() / (scale * got.shape[0]))
     return err_rows, err_proj, err_col

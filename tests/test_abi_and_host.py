@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), "librgnn.so does not export %s" % name
     lib.rgnn_version.restype = ctypes.c_int
-    assert lib.rgnn_version() == 100
+    assert lib.rgnn_version() == 200
     # every declared symbol has a ctypes signature in the binding and vice versa
     assert set(declared_symbols()) == set(engine.SIGNATURES) - (engine.OPTIONAL_SYMBOLS - set(declared_symbols()))
 

@@ -10,4 +10,6 @@ from .engine import GraphPlan, RgnnError, launch_count, set_weight_cache, weight
 from .gnns import (sparse_rgcn_layer, sparse_ggnn_layer, sparse_rgat_layer, sparse_rgin_layer,  # noqa: F401
                    sparse_gnn_edge_mlp_layer, sparse_gnn_film_layer, sparse_rgdcn_layer, rgcn_layer_stack)
 
-__version__ = "0.1.0"
+from .sharded import ShardedGraph, PeerBuffer, degree_balanced_cuts  # noqa: F401
+
+__version__ = "0.2.0"

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librgnn.so")
 STAMP = os.path.join(LIB_DIR, "librgnn.stamp")
-SOURCES = ["gemm_tf32x3.cu", "gemm_tcgen05.cu", "gemm_tn_tcgen05.cu", "plan.cu", "seg_kernels.cu", "layers.cu"]
+SOURCES = ["gemm_tcgen05.cu", "gemm_tn_tcgen05.cu", "plan.cu", "halo.cu", "seg_kernels.cu", "layers.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -43,15 +43,11 @@ struct GemmParams {
   int k_block = 0;                            // BATCH_K_BLOCKS_T: rows of K contributed by each bptr[z] (its column count)
 };
 
-// Enqueue; returns RGNN_OK / error code.  All dims % 4 == 0, pointers 16-byte aligned.
-// Legacy tensor path (mma.sync.m16n8k8.tf32): kept as the A/B reference of the tcgen05 kernel
-// (RGNN_GEMM_IMPL=mma); needs no scratch.
-int launch_gemm(const GemmParams& p, cudaStream_t stream);
-
 // Blackwell path (gemm_tcgen05.cu): tcgen05.mma.kind::tf32 with a TMEM accumulator.  Needs scratch for
 // the pre-swizzled hi/lo weight images (gemm_tc_pack_bytes).  The scratch may be reused as soon as the call
 // returns as long as later users are ordered on the same stream.
 size_t gemm_tc_pack_bytes(const GemmParams& p);
+size_t gemm_tc_pack_bytes_uncached(const GemmParams& p);   // what a call needs when the weight-image cache is off
 int launch_gemm_tcgen05(const GemmParams& p, void* pack_ws, size_t pack_ws_bytes, cudaStream_t stream);
 
 // Optional cache of the packed weight images (static weights).  See rgnn_set_weight_cache in include/rgnn.h.
@@ -70,8 +66,5 @@ struct GemmTnOut {
 size_t gemm_tn_scratch_floats(int M, int N, int K);
 int launch_gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const GemmTnOut& out,
                    float* scratch, cudaStream_t stream);
-
-// true unless the environment says RGNN_GEMM_IMPL=mma
-bool gemm_use_tcgen05();
 
 }  // namespace rgnn

@@ -484,6 +484,9 @@ bool gemm_weight_cache_enabled() { return g_pack_cache_on; }
 
 size_t gemm_tc_pack_bytes(const GemmParams& g) {
   if (g_pack_cache_on) return 1024;   // images live in the cache, the caller's scratch is not used
+  return gemm_tc_pack_bytes_uncached(g);
+}
+size_t gemm_tc_pack_bytes_uncached(const GemmParams& g) {
   const int chunks = (g.K1 + TC_BK - 1) / TC_BK + (g.K2 + TC_BK - 1) / TC_BK;
   const int n_total = (g.batch_mode == BATCH_SHARED_A) ? g.batch * g.N : g.N;
   const int gz = (g.batch_mode == BATCH_ROW_RANGES || g.batch_mode == BATCH_COL_BLOCKS) ? g.batch : 1;
@@ -599,13 +602,18 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   }
 
   const size_t smem = 1024 + (size_t)p.ring_bytes + EPI_STAGE_BYTES + (2 * p.stages + 4) * sizeof(uint64_t) + 16;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int device = 0;
-    cudaGetDevice(&device);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
-    if (num_sms <= 0) num_sms = 148;
+  // per-DEVICE launch state (a process may drive several GPUs): SM count, opt-in shared memory, resident clusters
+  constexpr int MAX_DEV = 64;
+  static int num_sms_of[MAX_DEV] = {};
+  int device = 0;
+  cudaGetDevice(&device);
+  const int dv = (device >= 0 && device < MAX_DEV) ? device : 0;
+  if (num_sms_of[dv] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    num_sms_of[dv] = n > 0 ? n : 148;
   }
+  const int num_sms = num_sms_of[dv];
   int max_clusters = num_sms / CL;
 
   using KernelFn = void (*)(TcParams);
@@ -623,10 +631,10 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
     }
   };
   KernelFn fn = pick(g.epi);
-  static bool attr_done[3][5] = {};
-  if (!attr_done[g.epi][CL]) {
+  static bool attr_done[MAX_DEV][3][5] = {};
+  if (!attr_done[dv][g.epi][CL]) {
     RGNN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
-    attr_done[g.epi][CL] = true;
+    attr_done[dv][g.epi][CL] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(TC_THREADS_V4);
@@ -638,7 +646,8 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   cfg.attrs = attr;
   cfg.numAttrs = (CL > 1) ? 1 : 0;   // plain launch when there is no cluster
   if (CL > 1) {   // clusters of 4 cannot use every SM (GPC sizes): size the persistent grid by what is co-resident
-    static int cached[3][5] = {};
+    static int cached_of[MAX_DEV][3][5] = {};
+    int (&cached)[3][5] = cached_of[dv];
     if (cached[g.epi][CL] == 0) {
       cfg.gridDim = dim3((unsigned)(max_clusters * CL));
       int n = 0;

@@ -258,10 +258,13 @@ int launch_gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int 
   int mt, splits;
   tn_shape(M, N, K, mt, p.n_tiles, splits, p.steps_per_split);
   p.steps_total = (K + TN_BK - 1) / TN_BK;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};   // per device
+  int device = 0;
+  cudaGetDevice(&device);
+  const int dv = (device >= 0 && device < 64) ? device : 0;
+  if (!attr_done[dv]) {
     RGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SMEM));
-    attr_done = true;
+    attr_done[dv] = true;
   }
   gemm_tn_tcgen05_kernel<<<dim3((unsigned)(mt * p.n_tiles), (unsigned)splits), TN_THREADS, TN_SMEM, stream>>>(p);
   RGNN_CHECK_CUDA(cudaGetLastError());

@@ -69,18 +69,6 @@ int check_agg(int agg, const char* who) {
   RGNN_REQUIRE(agg >= RGNN_AGG_SUM && agg <= RGNN_AGG_SQRT_N, "%s: Unknown aggregation function code %d", who, agg);
   return RGNN_OK;
 }
-bool g_use_tc = true;
-bool g_use_tc_init = false;
-}  // namespace
-bool gemm_use_tcgen05() {
-  if (!g_use_tc_init) {
-    const char* e = getenv("RGNN_GEMM_IMPL");
-    g_use_tc = !(e != nullptr && strcmp(e, "mma") == 0);
-    g_use_tc_init = true;
-  }
-  return g_use_tc;
-}
-namespace {
 int check_ws(const Arena& a, const char* who) {
   if (a.overflow) {
     set_error("%s: workspace too small (%zu bytes given, %zu needed)", who, a.cap, a.used);
@@ -89,10 +77,9 @@ int check_ws(const Arena& a, const char* who) {
   return RGNN_OK;
 }
 
-// Dispatch one dense contraction: tcgen05 kernel (weight images packed into arena scratch that is released
-// right after the enqueue -- later users are stream-ordered) or the legacy mma.sync kernel.
+// Dispatch one dense contraction on the tcgen05 kernel (weight images packed into arena scratch that is released
+// right after the enqueue -- later users are stream-ordered).
 int run_gemm(const GemmParams& g, Arena& ar, cudaStream_t stream) {
-  if (!gemm_use_tcgen05()) return launch_gemm(g, stream);
   const size_t need = gemm_tc_pack_bytes(g);
   const size_t mark = ar.used;
   void* ws = ar.floats(need / sizeof(float));
@@ -358,7 +345,6 @@ extern "C" int rgnn_rgcn_backward(const rgnn_plan_t* plan_c, const float* h, int
     return RGNN_E_UNSUPPORTED;
   }
   RGNN_REQUIRE(!normalize || num_incoming != nullptr, "rgcn_backward: normalize_by_num_incoming needs type_to_num_incoming_edges");
-  RGNN_REQUIRE(gemm_use_tcgen05(), "rgcn_backward needs the tcgen05 GEMM (unset RGNN_GEMM_IMPL=mma)");
   const int V = plan->V, L = plan->L;
   RGNN_PROPAGATE(plan_ensure_reverse(plan, stream));
   Arena ar(workspace, workspace_bytes);
@@ -825,50 +811,49 @@ extern "C" int rgnn_edge_aggregate_backward(const rgnn_plan_t* plan_c, const flo
   return rc;
 }
 
+// Scratch of rgnn_dense_forward / rgnn_dense_backward: the weight images of the contraction(s) + the split-K partial tiles.
+extern "C" size_t rgnn_dense_workspace_bytes(int32_t m, int32_t k, int32_t n) {
+  if (m < 0 || k <= 0 || n <= 0) return 0;
+  GemmParams f;
+  f.M = m; f.N = n; f.K1 = k; f.lda1 = k; f.ldb1 = n; f.ldc = n;
+  GemmParams t;
+  t.M = m; t.N = k; t.K1 = n; t.lda1 = n; t.ldb1 = n; t.ldc = k; t.batch_mode = BATCH_K_BLOCKS_T; t.batch = 1; t.k_block = n;
+  const size_t pack = gemm_tc_pack_bytes_uncached(f) > gemm_tc_pack_bytes_uncached(t) ? gemm_tc_pack_bytes_uncached(f) : gemm_tc_pack_bytes_uncached(t);
+  return align_up(pack, 256) + align_up(gemm_tn_scratch_floats(k, n, m) * sizeof(float), 256) + 512;
+}
+
 extern "C" int rgnn_dense_forward(const float* a, int32_t m, int32_t k, const float* b, int32_t n, const float* bias,
-                                  int activation, float* c, void* stream_) {
+                                  int activation, float* c, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RGNN_REQUIRE(a && b && c, "dense: NULL argument");
   RGNN_PROPAGATE(check_act(activation, "dense"));
   GemmParams g;
   g.A1 = a; g.lda1 = k; g.K1 = k; g.B1 = b; g.ldb1 = n; g.M = m; g.N = n; g.C = c; g.ldc = n;
   g.bias = bias; g.act = activation;
-  if (!gemm_use_tcgen05()) return launch_gemm(g, stream);
-  const size_t need = gemm_tc_pack_bytes(g);
-  void* ws = nullptr;
-  RGNN_CHECK_CUDA(cudaMallocAsync(&ws, need, stream));
-  const int rc = launch_gemm_tcgen05(g, ws, need, stream);
-  cudaFreeAsync(ws, stream);
-  return rc;
+  Arena ar(workspace, workspace_bytes);
+  return run_gemm(g, ar, stream);
 }
 
 // gradients of the linear map C = A . B of rgnn_dense_forward (TF autodiff of tf.keras Dense, sparse_graph_model.py:253)
 extern "C" int rgnn_dense_backward(const float* a, int32_t m, int32_t k, const float* b, int32_t n, const float* grad_c,
-                                   float* grad_a, float* grad_b, void* stream_) {
+                                   float* grad_a, float* grad_b, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RGNN_REQUIRE((grad_c != nullptr || m == 0) && m >= 0 && k > 0 && n > 0 && (k % 4) == 0 && (n % 4) == 0, "dense_backward: bad arguments (m=%d k=%d n=%d)", m, k, n);
-  RGNN_REQUIRE(gemm_use_tcgen05(), "dense_backward needs the tcgen05 GEMM (unset RGNN_GEMM_IMPL=mma)");
+  Arena ar(workspace, workspace_bytes);
   if (grad_a != nullptr && m > 0) {   // dA = dC . B^T
     RGNN_REQUIRE(b != nullptr, "dense_backward: grad_a needs b");
     GemmParams g;
     g.A1 = grad_c; g.lda1 = n; g.K1 = n; g.M = m; g.N = k; g.C = grad_a; g.ldc = k; g.ldb1 = n;
     g.batch_mode = BATCH_K_BLOCKS_T; g.batch = 1; g.k_block = n; g.bptr[0] = b; g.bptr2[0] = nullptr;
-    const size_t need = gemm_tc_pack_bytes(g);
-    void* ws = nullptr;
-    RGNN_CHECK_CUDA(cudaMallocAsync(&ws, need, stream));
-    const int rc = launch_gemm_tcgen05(g, ws, need, stream);
-    cudaFreeAsync(ws, stream);
-    RGNN_PROPAGATE(rc);
+    RGNN_PROPAGATE(run_gemm(g, ar, stream));
   }
   if (grad_b != nullptr) {            // dB = A^T . dC
     RGNN_REQUIRE(a != nullptr || m == 0, "dense_backward: grad_b needs a");
     GemmTnOut tn;
     tn.block_cols = n; tn.ld = n; tn.ptr[0] = grad_b;
-    void* ws = nullptr;
-    RGNN_CHECK_CUDA(cudaMallocAsync(&ws, gemm_tn_scratch_floats(k, n, m) * sizeof(float), stream));
-    const int rc = launch_gemm_tn(a, k, grad_c, n, k, n, m, tn, static_cast<float*>(ws), stream);
-    cudaFreeAsync(ws, stream);
-    RGNN_PROPAGATE(rc);
+    float* ws = ar.floats(gemm_tn_scratch_floats(k, n, m));
+    RGNN_PROPAGATE(check_ws(ar, "dense_backward"));
+    RGNN_PROPAGATE(launch_gemm_tn(a, k, grad_c, n, k, n, m, tn, ws, stream));
   }
   return RGNN_OK;
 }

@@ -65,9 +65,23 @@ SIGNATURES = {
     "rgnn_segment_aggregate": (c_int, [_PTR, _PTR, c_int32, c_int, _PTR, _PTR]),
     "rgnn_edge_aggregate_forward": (c_int, [_PTR, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
     "rgnn_edge_aggregate_backward": (c_int, [_PTR, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
-    "rgnn_dense_forward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, c_int, _PTR, _PTR]),
-    "rgnn_dense_backward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, _PTR, _PTR, _PTR]),
+    "rgnn_dense_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "rgnn_dense_forward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, c_int, _PTR, _PTR, c_size_t, _PTR]),
+    "rgnn_dense_backward": (c_int, [_PTR, c_int32, c_int32, _PTR, c_int32, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
     "rgnn_layer_norm": (c_int, [_PTR, c_int32, c_int32, _PTR, _PTR, _PTR, _PTR]),
+    "rgnn_halo_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int32, c_int32, _PTR, c_int32, _PTR, _PTR, _PTR]),
+    "rgnn_halo_plan_destroy": (c_int, [_PTR]),
+    "rgnn_halo_plan_num_own": (c_int32, [_PTR]),
+    "rgnn_halo_plan_num_halo": (c_int32, [_PTR]),
+    "rgnn_halo_plan_num_edges": (c_int64, [_PTR, c_int32]),
+    "rgnn_halo_plan_graph": (c_void_p, [_PTR]),
+    "rgnn_halo_plan_export": (c_int, [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "rgnn_halo_plan_attach": (c_int, [_PTR, _PTR, _PTR, _PTR]),
+    "rgnn_halo_exchange": (c_int, [_PTR, c_int, c_int32, _PTR]),
+    "rgnn_peer_alloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t, _PTR]),
+    "rgnn_peer_open": (c_int, [_PTR, ctypes.POINTER(c_void_p)]),
+    "rgnn_peer_close": (c_int, [_PTR]),
+    "rgnn_peer_free": (c_int, [_PTR]),
     "rgnn_rgcn_stack_forward": (c_int, [_PTR, _PTR, c_int32, c_int32, _PTR, _PTR, c_int, c_int, c_int,
                                         _PTR, _PTR, c_size_t, _PTR]),
 }
@@ -123,13 +137,15 @@ def launch_count() -> int:
 
 
 _weight_cache_on = False
-_weight_versions: Dict[int, int] = {}
+# data_ptr -> (Tensor._version, weakref to the tensor that owns the memory) of every weight passed down while the cache is on
+_weight_versions: Dict[int, tuple] = {}
 
 
 def set_weight_cache(enable: bool):
     """Static-weight mode (inference / benchmarking): keep the GEMM's packed weight images across calls
-    (rgnn_set_weight_cache in include/rgnn.h).  In-place updates of weight tensors are detected through
-    ``Tensor._version`` the next time they are passed to a layer function and flush the cache."""
+    (rgnn_set_weight_cache in include/rgnn.h).  The library keys the images on device POINTERS; this layer makes that
+    safe: an in-place update (``Tensor._version`` changed) or the death of the tensor that owned a cached address
+    (its memory may since belong to a different weight) flushes the cache the next time that address is passed down."""
     global _weight_cache_on
     check(load_library().rgnn_set_weight_cache(1 if enable else 0))
     _weight_cache_on = bool(enable)
@@ -141,17 +157,34 @@ def weight_cache_clear():
     _weight_versions.clear()
 
 
+def _owner(t: torch.Tensor) -> torch.Tensor:
+    """The tensor whose lifetime bounds the memory ``t`` points into (a view's base)."""
+    base = t._base
+    return base if base is not None else t
+
+
 def note_weights(tensors):
-    """Called by the layer functions with every weight tensor they are about to pass down."""
+    """Called by the layer functions with every WEIGHT tensor they are about to pass down (not with adjacency lists or
+    gradient buffers)."""
     if not _weight_cache_on:
         return
+    import weakref
     stale = False
     for t in tensors:
         key, ver = t.data_ptr(), t._version
         old = _weight_versions.get(key)
-        if old is not None and old != ver:
+        if old is not None:
+            old_ver, old_ref = old
+            owner = old_ref()
+            # a dead owner means the address may have been recycled for a different weight; a live but different owner at
+            # the same address IS a different allocation (two live tensors cannot overlap unless they share a base)
+            if owner is None or old_ver != ver or owner is not _owner(t):
+                stale = True
+        _weight_versions[key] = (ver, weakref.ref(_owner(t)))
+    if len(_weight_versions) > 4096:                      # forget addresses whose owners are gone
+        for k in [k for k, (_, r) in _weight_versions.items() if r() is None]:
             stale = True
-        _weight_versions[key] = ver
+            del _weight_versions[k]
     if stale:
         check(load_library().rgnn_weight_cache_clear())
 
@@ -175,27 +208,31 @@ def as_f32(t: torch.Tensor, what: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
-def ptr_table(tensors: Sequence[torch.Tensor]):
-    """Host array of device pointers (the 'host array of L device pointers' of include/rgnn.h)."""
-    note_weights(tensors)
+def ptr_table(tensors: Sequence[torch.Tensor], weights: bool = True):
+    """Host array of device pointers (the 'host array of L device pointers' of include/rgnn.h).  ``weights=False`` for
+    tables that are not layer weights (adjacency lists, gradient buffers): those never enter the weight-image cache."""
+    if weights:
+        note_weights(tensors)
     arr = (c_void_p * max(len(tensors), 1))()
     for i, t in enumerate(tensors):
         arr[i] = t.data_ptr()
     return arr
 
 
-_workspaces: Dict[int, torch.Tensor] = {}
-
-
 def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Grow-only scratch buffer per device (stream-ordered reuse is safe: all work is enqueued on the
-    current stream in program order)."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
-    buf = _workspaces.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = buf
-    return buf
+    """Scratch for one library call, from torch's caching allocator.  One allocation per call (not a grow-only global
+    buffer): the allocator is stream-ordered and capture-safe, so a block recorded into a CUDA graph stays owned by that
+    graph's private pool and a later, larger request can never hand it to somebody else (a replayed graph was
+    writing into a freed global workspace); callers on several streams get distinct blocks."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def output_rows(plan: "GraphPlan", dim: int, device) -> torch.Tensor:
+    """[V, dim] result buffer of a layer call.  Kernels write rows [0, num_targets) only (rgnn_plan_set_num_targets): on a
+    restricted plan the remaining (halo) rows are zero-filled so that nothing downstream reads uninitialised memory."""
+    if getattr(plan, "num_targets", plan.num_nodes) < plan.num_nodes:
+        return torch.zeros((plan.num_nodes, dim), dtype=torch.float32, device=device)
+    return torch.empty((plan.num_nodes, dim), dtype=torch.float32, device=device)
 
 
 class GraphPlan:
@@ -236,13 +273,28 @@ class GraphPlan:
         self.num_nodes = int(num_nodes)
         self.num_edge_types = len(dev_adj)
         counts = (c_int64 * max(len(dev_adj), 1))(*[int(a.shape[0]) for a in dev_adj])
-        ptrs = ptr_table(dev_adj)
+        ptrs = ptr_table(dev_adj, weights=False)
         handle = c_void_p()
         with torch.cuda.device(device):
             check(lib.rgnn_plan_create_ex(ctypes.byref(handle), self.num_nodes, self.num_edge_types, ptrs, counts,
                                           0 if validate else 1, current_stream_ptr(device)))
         self._handle = handle
         self.num_edges = int(lib.rgnn_plan_num_edges(handle))
+
+    @classmethod
+    def from_handle(cls, handle, num_nodes: int, num_edge_types: int, num_edges: int, device, num_targets=None,
+                    owner=None, adjacency_lists=None) -> "GraphPlan":
+        """Wrap an rgnn_plan_t that somebody else owns (rgnn_halo_plan_graph): usable wherever a GraphPlan is, never
+        destroyed by this object; ``owner`` is kept alive with it."""
+        self = cls.__new__(cls)
+        self.device = torch.device(device)
+        self.adjacency_lists = adjacency_lists
+        self.num_nodes, self.num_edge_types, self.num_edges = int(num_nodes), int(num_edge_types), int(num_edges)
+        self._handle = c_void_p(handle) if not isinstance(handle, c_void_p) else handle
+        self._borrowed, self._owner = True, owner
+        if num_targets is not None:
+            self.num_targets = int(num_targets)
+        return self
 
     @property
     def handle(self):
@@ -337,7 +389,8 @@ class GraphPlan:
 
     def close(self):
         if getattr(self, "_handle", None) is not None:
-            load_library().rgnn_plan_destroy(self._handle)
+            if not getattr(self, "_borrowed", False):
+                load_library().rgnn_plan_destroy(self._handle)
             self._handle = None
 
     def __del__(self):

@@ -42,6 +42,14 @@ def requires_grad(*objs) -> bool:
     return any(walk(o) for o in objs)
 
 
+def _check_restricted(plan: GraphPlan, num_timesteps: int):
+    """A plan restricted to its first num_targets rows (one rank of a node-range partition) updates only those rows: the
+    halo rows must be refreshed by the caller's exchange between steps, so -- like the C ABI -- only one timestep per call."""
+    if getattr(plan, "num_targets", plan.num_nodes) < plan.num_nodes and int(num_timesteps) != 1:
+        raise RgnnError(RGNN_E_INVALID, "a plan restricted to %d of %d target rows supports num_timesteps == 1 only"
+                        % (plan.num_targets, plan.num_nodes))
+
+
 def _layer_norm(x, gamma, beta):
     return torch.nn.functional.layer_norm(x, (x.shape[1],), gamma, beta, 1e-12)     # tf.contrib.layers.layer_norm (A.5)
 
@@ -83,6 +91,7 @@ def _per_type_mlp(mlps, x, plan: GraphPlan, hidden_act):
 
 # ---- gnns/rgcn.py:84-114 for the settings the fused backward does not cover (max aggregation / [h_u | h_v] messages) ----
 def rgcn(h, plan, cnt, ws, act_code, aggregation, use_both, num_timesteps):
+    _check_restricted(plan, num_timesteps)
     act = _ACT[act_code]
     L, d_out = plan.num_edge_types, ws[0].shape[1]
     cur = h
@@ -101,6 +110,7 @@ def rgcn(h, plan, cnt, ws, act_code, aggregation, use_both, num_timesteps):
 
 # ---- gnns/ggnn.py:71-93 ----
 def ggnn(h, plan, ws, cell, cell_kind: str, act_code, aggregation, num_timesteps):
+    _check_restricted(plan, num_timesteps)
     act = _ACT[act_code]
     L, d = plan.num_edge_types, h.shape[1]
     K, R, B = cell["kernel"], cell["recurrent_kernel"], cell["bias"]
@@ -122,6 +132,7 @@ def ggnn(h, plan, ws, cell, cell_kind: str, act_code, aggregation, num_timesteps
 
 # ---- gnns/rgat.py:83-138 ----
 def rgat(h, plan, ws, att, num_heads: int, act_code, num_timesteps):
+    _check_restricted(plan, num_timesteps)
     act = _ACT[act_code]
     L, V = plan.num_edge_types, plan.num_nodes
     D = ws[0].shape[1]
@@ -150,6 +161,7 @@ def rgat(h, plan, ws, att, num_heads: int, act_code, num_timesteps):
 
 # ---- gnns/gnn_film.py:85-120 ----
 def film(h, plan, cnt, ws, fws, ln, act_code, aggregation, num_timesteps):
+    _check_restricted(plan, num_timesteps)
     act = _ACT[act_code]
     L, V, D = plan.num_edge_types, plan.num_nodes, ws[0].shape[1]
     w_cat, f_cat = torch.cat(list(ws), dim=1), torch.cat(list(fws), dim=1)
@@ -167,6 +179,7 @@ def film(h, plan, cnt, ws, fws, ln, act_code, aggregation, num_timesteps):
 
 # ---- gnns/gnn_edge_mlp.py:84-119 ----
 def edge_mlp(h, plan, cnt, mlps, ln, act_code, aggregation, use_target: bool, num_timesteps):
+    _check_restricted(plan, num_timesteps)
     act, elu = _ACT[act_code], torch.nn.functional.elu
     D = mlps[0][-1].shape[1]
     scale = _message_scale(plan, cnt)
@@ -185,6 +198,7 @@ def edge_mlp(h, plan, cnt, mlps, ln, act_code, aggregation, use_target: bool, nu
 
 # ---- gnns/rgin.py:103-139 ----
 def rgin(h, plan, mlps, aggr_mlp, ln, act_code, aggregation, use_target: bool, num_timesteps):
+    _check_restricted(plan, num_timesteps)
     act = _ACT[act_code]
     L, V = plan.num_edge_types, plan.num_nodes
     cur = h

@@ -5,6 +5,7 @@ import torch
 
 from ..utils import LAYER_GGNN, CELL_GRU, get_aggregation_function, get_gated_unit
 from ..engine import note_weights
+from ..engine import output_rows
 from ._common import (RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, load_library, prepare, ptr_table,
                       weight_list, workspace)
 from . import _train
@@ -45,7 +46,7 @@ def sparse_ggnn_layer(node_embeddings: torch.Tensor,
                            "gru" if cell_kind == CELL_GRU else "rnn", act, message_aggregation_function, num_timesteps)
     note_weights([kernel, rec, bias])
     lib = load_library()
-    out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
+    out = output_rows(plan, d_out, h.device)
     with torch.cuda.device(h.device):
         nbytes = lib.rgnn_workspace_bytes(plan.handle, LAYER_GGNN, d_in, d_out, 0)
         ws_buf = workspace(h.device, nbytes)

@@ -4,6 +4,7 @@ from typing import Dict, Optional
 import torch
 
 from ..utils import LAYER_EDGE_MLP, get_activation, get_aggregation_function
+from ..engine import output_rows
 from ._common import (RgnnError, RGNN_E_INVALID, check, current_stream_ptr, int32_array, layer_norm_params,
                       load_library, mlp_tables, num_incoming_tensor, prepare, ptr_table, workspace)
 from . import _train
@@ -44,7 +45,7 @@ def sparse_gnn_edge_mlp_layer(node_embeddings: torch.Tensor,
         return _train.edge_mlp(h, plan, cnt, per_type, (g, b), act, message_aggregation_function,
                                bool(use_target_state_as_input), num_timesteps)
     lib = load_library()
-    out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
+    out = output_rows(plan, d_out, h.device)
     with torch.cuda.device(h.device):
         nbytes = lib.rgnn_workspace_bytes(plan.handle, LAYER_EDGE_MLP, d_in, d_out, nl)
         ws_buf = workspace(h.device, nbytes)

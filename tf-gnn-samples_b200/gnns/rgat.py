@@ -4,6 +4,7 @@ from typing import Dict, Optional
 import torch
 
 from ..utils import LAYER_RGAT, get_activation
+from ..engine import output_rows
 from ._common import (check, current_stream_ptr, load_library, prepare, ptr_table, weight_list, workspace)
 from . import _train
 
@@ -33,7 +34,7 @@ def sparse_rgat_layer(node_embeddings: torch.Tensor,
     if _train.requires_grad(h, ws, att):                              # training: differentiable composition (gnns/_train.py)
         return _train.rgat(h, plan, ws, att, int(num_heads), act, num_timesteps)
     lib = load_library()
-    out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
+    out = output_rows(plan, d_out, h.device)
     with torch.cuda.device(h.device):
         nbytes = lib.rgnn_workspace_bytes(plan.handle, LAYER_RGAT, d_in, d_out, 0)
         ws_buf = workspace(h.device, nbytes)

@@ -4,6 +4,7 @@ from typing import Dict, List, Optional
 import torch
 
 from ..utils import AGG_MAX, LAYER_RGCN, LAYER_RGCN_BACKWARD, get_activation, get_aggregation_function
+from ..engine import output_rows
 from ._common import (check, current_stream_ptr, load_library, num_incoming_tensor, prepare, ptr_table, weight_list,
                       workspace)
 from . import _train
@@ -11,7 +12,7 @@ from . import _train
 
 def _forward_raw(h, plan, cnt, ws, d_in, d_out, act, agg, normalize, both, num_timesteps):
     lib = load_library()
-    out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
+    out = output_rows(plan, d_out, h.device)
     with torch.cuda.device(h.device):
         nbytes = lib.rgnn_workspace_bytes(plan.handle, LAYER_RGCN, d_in, d_out, 0)
         ws_buf = workspace(h.device, nbytes)
@@ -54,7 +55,7 @@ class _RGCNStep(torch.autograd.Function):
                                          cnt.data_ptr() if cnt is not None else None, ctx.act, ctx.agg,
                                          int(bool(ctx.normalize)), out.data_ptr(), g.data_ptr(),
                                          grad_h.data_ptr() if need_h else None,
-                                         ptr_table(grad_ws) if need_w else None,
+                                         ptr_table(grad_ws, weights=False) if need_w else None,
                                          ws_buf.data_ptr(), ws_buf.numel(), current_stream_ptr(h.device)))
         return (grad_h, None, None, None, None, None) + (tuple(grad_ws) if need_w else tuple(None for _ in ws))
 
@@ -115,7 +116,7 @@ def rgcn_layer_stack(node_embeddings: torch.Tensor, adjacency_lists, type_to_num
         flat.extend(weight_list(w, "edge_weights", L, (d_in, d_in), "rgcn_layer_stack"))
     cnt = num_incoming_tensor(type_to_num_incoming_edges, plan, normalize_by_num_incoming)
     lib = load_library()
-    out = torch.empty((plan.num_nodes, d_in), dtype=torch.float32, device=h.device)
+    out = output_rows(plan, d_in, h.device)
     with torch.cuda.device(h.device):
         nbytes = lib.rgnn_workspace_bytes(plan.handle, LAYER_RGCN, d_in, d_in, 0) + 2 * (plan.num_nodes * d_in * 4 + 256)
         ws_buf = workspace(h.device, nbytes)

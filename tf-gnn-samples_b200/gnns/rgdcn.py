@@ -4,6 +4,7 @@ from typing import Dict, List, Optional
 import torch
 
 from ..utils import LAYER_RGDCN, get_activation, get_aggregation_function
+from ..engine import output_rows
 from ._common import (RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, load_library, num_incoming_tensor, prepare,
                       ptr_table, workspace)
 from . import _train
@@ -56,7 +57,7 @@ def sparse_rgdcn_layer(node_embeddings: torch.Tensor,
         raise RgnnError(RGNN_E_INVALID, "sparse_rgdcn_layer has no gradient path in this build; call it under torch.no_grad()")
     cnt = num_incoming_tensor(type_to_num_incoming_edges, plan, normalize_by_num_incoming)
     lib = load_library()
-    out = torch.empty((plan.num_nodes, d_in), dtype=torch.float32, device=h.device)
+    out = output_rows(plan, d_in, h.device)
     with torch.cuda.device(h.device):
         nbytes = lib.rgnn_workspace_bytes(plan.handle, LAYER_RGDCN, d_in, d_in, K)
         ws_buf = workspace(h.device, nbytes)

@@ -4,6 +4,7 @@ from typing import Dict, Optional
 import torch
 
 from ..utils import LAYER_RGIN, get_activation, get_aggregation_function
+from ..engine import output_rows
 from ._common import (RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, int32_array, layer_norm_params,
                       load_library, mlp_tables, prepare, ptr_table, workspace)
 from . import _train
@@ -56,7 +57,7 @@ def sparse_rgin_layer(node_embeddings: torch.Tensor,
         return _train.rgin(h, plan, per_type, aggr_keep if aggr_ptrs is not None else None, (g, b), act,
                            message_aggregation_function, bool(use_target_state_as_input), num_timesteps)
     lib = load_library()
-    out = torch.empty((plan.num_nodes, d_out), dtype=torch.float32, device=h.device)
+    out = output_rows(plan, d_out, h.device)
     with torch.cuda.device(h.device):
         nbytes = lib.rgnn_workspace_bytes(plan.handle, LAYER_RGIN, d_in, d_out, max(nl_edge, nl_aggr))
         ws_buf = workspace(h.device, nbytes)

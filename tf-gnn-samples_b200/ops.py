@@ -4,7 +4,7 @@ from typing import Optional
 
 import torch
 
-from .engine import GraphPlan, RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, load_library
+from .engine import GraphPlan, RgnnError, RGNN_E_INVALID, as_f32, check, current_stream_ptr, load_library, output_rows, workspace
 from .utils import get_activation, get_aggregation_function
 from .utils import AGG_MAX, AGG_MEAN, AGG_SQRT_N, AGG_SUM
 from .utils import (ACT_ELU, ACT_GELU, ACT_LEAKY_RELU, ACT_LINEAR, ACT_RELU, ACT_SELU, ACT_TANH)
@@ -19,10 +19,12 @@ _TORCH_ACT = {
 
 def _dense_raw(x, kernel, b, act_code):
     out = torch.empty((x.shape[0], kernel.shape[1]), dtype=torch.float32, device=x.device)
+    lib = load_library()
     with torch.cuda.device(x.device):
-        check(load_library().rgnn_dense_forward(x.data_ptr(), x.shape[0], x.shape[1], kernel.data_ptr(), kernel.shape[1],
-                                                b.data_ptr() if b is not None else None, act_code,
-                                                out.data_ptr(), current_stream_ptr(x.device)))
+        ws = workspace(x.device, lib.rgnn_dense_workspace_bytes(x.shape[0], x.shape[1], kernel.shape[1]))
+        check(lib.rgnn_dense_forward(x.data_ptr(), x.shape[0], x.shape[1], kernel.data_ptr(), kernel.shape[1],
+                                     b.data_ptr() if b is not None else None, act_code,
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), current_stream_ptr(x.device)))
     return out
 
 
@@ -33,10 +35,13 @@ def dense_backward(x: torch.Tensor, kernel: torch.Tensor, grad_out: torch.Tensor
     x, kernel, g = as_f32(x, "x"), as_f32(kernel, "kernel"), as_f32(grad_out, "grad_out")
     gx = torch.empty_like(x) if need_x else None
     gk = torch.empty_like(kernel) if need_kernel else None
+    lib = load_library()
     with torch.cuda.device(x.device):
-        check(load_library().rgnn_dense_backward(x.data_ptr(), x.shape[0], x.shape[1], kernel.data_ptr(), kernel.shape[1],
-                                                 g.data_ptr(), gx.data_ptr() if need_x else None,
-                                                 gk.data_ptr() if need_kernel else None, current_stream_ptr(x.device)))
+        ws = workspace(x.device, lib.rgnn_dense_workspace_bytes(x.shape[0], x.shape[1], kernel.shape[1]))
+        check(lib.rgnn_dense_backward(x.data_ptr(), x.shape[0], x.shape[1], kernel.data_ptr(), kernel.shape[1],
+                                      g.data_ptr(), gx.data_ptr() if need_x else None,
+                                      gk.data_ptr() if need_kernel else None, ws.data_ptr(), ws.numel(),
+                                      current_stream_ptr(x.device)))
     return gx, gk
 
 
@@ -77,7 +82,7 @@ def dense(x: torch.Tensor, kernel: torch.Tensor, bias: Optional[torch.Tensor] = 
 
 
 def _segment_raw(plan: GraphPlan, data: torch.Tensor, agg_code: int) -> torch.Tensor:
-    out = torch.empty((plan.num_nodes, data.shape[1]), dtype=torch.float32, device=data.device)
+    out = output_rows(plan, data.shape[1], data.device)
     if data.shape[0] == 0:            # no messages: an empty tensor has no device pointer; the kernel never dereferences it
         data = torch.zeros((1, data.shape[1]), dtype=torch.float32, device=data.device)
     with torch.cuda.device(data.device):
@@ -132,7 +137,7 @@ class _EdgeAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table, plan, cnt, agg_code):
         V, L, d = table.shape
-        out = torch.empty((V, d), dtype=torch.float32, device=table.device)
+        out = output_rows(plan, d, table.device)
         with torch.cuda.device(table.device):
             check(load_library().rgnn_edge_aggregate_forward(plan.handle, table.data_ptr(), d,
                                                              cnt.data_ptr() if cnt is not None else None, agg_code,
