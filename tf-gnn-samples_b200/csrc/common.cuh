@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/rgnn.h"
 
@@ -97,6 +98,27 @@ __device__ __forceinline__ float4 act4(float4 v, int act) {
 __device__ __forceinline__ float4 act4_cold(float4 v, int act) {
   if (act == RGNN_ACT_LINEAR) return v;
   return slow_act4(v, act);
+}
+
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has
+// COMPLETED and its writes are visible (no-op for a normal launch), so everything before it (barrier init, TMEM allocation,
+// reads of per-batch plan arrays) overlaps the predecessor's tail.  pdl_launch_dependents() lets the successor start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Launch `kernel<<<grid, block, smem, stream>>>(params)` as a programmatic dependent of the previous kernel in the stream.
+// Only for kernels that call pdl_wait() before touching anything an earlier kernel produced or still reads.
+template <typename Params>
+static inline cudaError_t launch_pdl(void (*kernel)(Params), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Params& params) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = getenv("RGNN_NO_PDL") != nullptr;   // A/B knob: plain stream-ordered launches
+  cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
 // read-only 128-bit load through the non-coherent path (tables written by a previous kernel)

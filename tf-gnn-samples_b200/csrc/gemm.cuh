@@ -41,6 +41,7 @@ struct GemmParams {
   int row_off[RGNN_MAX_EDGE_TYPES + 1];       // BATCH_ROW_RANGES
   int max_rows = 0;                           // max rows of any batch entry (grid sizing)
   int k_block = 0;                            // BATCH_K_BLOCKS_T: rows of K contributed by each bptr[z] (its column count)
+  const int32_t* a_rows = nullptr;            // gathered A: output row r reads A1 row a_rows[r] (compact (source, type) transform)
 };
 
 // Blackwell path (gemm_tcgen05.cu): tcgen05.mma.kind::tf32 with a TMEM accumulator.  Needs scratch for

@@ -274,6 +274,11 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   tc_fence_after_sync();
   const uint32_t tmem_base = lds32(tmem_slot);
   if (tid == 0) TC_TRACE(1);
+  // Everything above (barrier init, TMEM allocation) touched only this CTA's own state and may have run while the previous
+  // kernel of the stream was still finishing (programmatic dependent launch); A, the weight images and C must not be touched
+  // before that kernel has completed.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp >= PROD_WARP0 && warp < MMA_WARP) {
     // =========================== A producers ===========================
@@ -297,8 +302,9 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
         const int f = ptid + i * TC_GROUP_THREADS;
         const int row = f >> 3, c16 = f & 7;
         const int grow = ti.m0 + row, gk = k0 + c16 * 4;
-        v[i] = (grow < ti.row_end && gk < Kseg) ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)grow * lda + gk))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool in = grow < ti.row_end && gk < Kseg;
+        const int arow = (in && g.a_rows != nullptr && !seg2) ? __ldg(g.a_rows + grow) : grow;   // gathered A (index list hits L1 after the first chunk)
+        v[i] = in ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)arow * lda + gk)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     float4 va[8];
@@ -640,11 +646,21 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   cfg.blockDim = dim3(TC_THREADS_V4);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  static const bool pdl_off = getenv("RGNN_NO_PDL") != nullptr;   // A/B knob
+  int na = 0;
+  if (!pdl_off) {   // the kernel calls pdl_wait() after its set-up: its prologue overlaps the previous kernel's tail
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (CL > 1) ? 1 : 0;   // plain launch when there is no cluster
+  cfg.numAttrs = na;
   if (CL > 1) {   // clusters of 4 cannot use every SM (GPC sizes): size the persistent grid by what is co-resident
     static int cached_of[MAX_DEV][3][5] = {};
     int (&cached)[3][5] = cached_of[dv];

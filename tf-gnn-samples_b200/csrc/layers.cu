@@ -106,6 +106,29 @@ int gemm_shared_a(Arena& ar, const float* A, int V, int K, const float* const* B
   return run_gemm(g, ar, stream);
 }
 
+// The per-type Dense on the SOURCE side of the edge stage (rgcn.py:98, ggnn.py:80-82, gnn_film.py:94 applied to nodes).
+// Dense form: T[V, L, D] = cur . [W_0|..|W_{L-1}].  Sparsely typed graphs (the plan holds a compact pair table, plan.cuh):
+// only the (source, type) rows that some edge gathers are transformed -- a row-range GEMM per type whose A rows follow the
+// pair list -- and the edge stage addresses the compact table.  Call after seg_from_plan(s, plan).
+int transform_sources(const rgnn_plan_t* plan, Arena& ar, const float* cur, int d_in, int D, const float* const* W, float* T,
+                      cudaStream_t stream, SegParams& s) {
+  const int V = plan->V, L = plan->L;
+  if (plan->n_pairs >= 0 && plan->pair_src != nullptr) {
+    GemmParams g;
+    g.A1 = cur; g.lda1 = d_in; g.K1 = d_in; g.a_rows = plan->pair_src;
+    g.M = plan->n_pairs; g.N = D; g.C = T; g.ldc = D; g.ldb1 = D;
+    g.batch_mode = BATCH_ROW_RANGES; g.batch = L; g.max_rows = plan->max_type_pairs;
+    for (int l = 0; l < L; ++l) { g.bptr[l] = W[l]; g.bptr2[l] = nullptr; g.row_off[l] = plan->pair_type_off[l]; }
+    g.row_off[L] = plan->pair_type_off[L];
+    RGNN_PROPAGATE(run_gemm(g, ar, stream));
+    s.table = T; s.e_idx = plan->e_pair; s.stride_idx = D; s.stride_type = 0;
+    return RGNN_OK;
+  }
+  RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, d_in, W, L, D, D, T, RGNN_ACT_LINEAR, stream));
+  s.table = T; s.stride_idx = (long)L * D; s.stride_type = D;
+  return RGNN_OK;
+}
+
 void seg_from_plan(SegParams& s, const rgnn_plan_t* plan) {
   s.V = plan->Vt; s.L = plan->L; s.scale_ld = plan->V;   // only the wanted target rows are reduced (rgnn_plan_set_num_targets)
   s.heavy_list = plan->heavy_list; s.heavy_count = plan->err_flag + 1;
@@ -308,10 +331,15 @@ extern "C" int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* h, int32_
       bp[l] = edge_weights[l];                                                // kernel rows [0, d_in): source half
       if (both) bp[L + l] = edge_weights[l] + (size_t)din * d_out;            // rows [d_in, 2 d_in): target half (rgcn.py:95)
     }
-    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, bp, nb, d_out, d_out, T, RGNN_ACT_LINEAR, stream));   // rgcn.py:98 on nodes
     SegParams s;
     seg_from_plan(s, plan);
-    s.D = d_out; s.table = T; s.stride_idx = (long)nb * d_out; s.stride_type = d_out;
+    s.D = d_out;
+    if (both) {
+      RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, bp, nb, d_out, d_out, T, RGNN_ACT_LINEAR, stream));   // rgcn.py:98 on nodes
+      s.table = T; s.stride_idx = (long)nb * d_out; s.stride_type = d_out;
+    } else {
+      RGNN_PROPAGATE(transform_sources(plan, ar, cur, din, d_out, bp, T, stream, s));                     // rgcn.py:98 on the used (source, type) rows
+    }
     s.num_incoming = normalize ? num_incoming : nullptr;                      // rgcn.py:100-104
     if (both) { s.msg_mode = MSG_ADDTGT; s.mod_table = T + (size_t)L * d_out; s.mod_stride_node = (long)nb * d_out; s.mod_stride_type = d_out; }
     s.agg = aggregation; s.act_out = activation;                              // rgcn.py:110,114
@@ -510,10 +538,10 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
   const float* cur = h;
   for (int t = 0; t < num_timesteps; ++t) {                                   // ggnn.py:71
     float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
-    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, D, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));   // ggnn.py:80-82
     SegParams s;
     seg_from_plan(s, plan);
-    s.D = D; s.table = T; s.stride_idx = (long)L * D; s.stride_type = D;
+    s.D = D;
+    RGNN_PROPAGATE(transform_sources(plan, ar, cur, D, D, edge_weights, T, stream, s));   // ggnn.py:80-82
     s.agg = aggregation; s.out = m; s.ld_out = D;                             // ggnn.py:87-90
     RGNN_PROPAGATE(launch_seg_reduce(s, stream));
     GemmParams g;
@@ -613,11 +641,11 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
   int din = d_in;
   for (int t = 0; t < num_timesteps; ++t) {                                   // gnn_film.py:85
     float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
-    RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));        // :94 on nodes
-    RGNN_PROPAGATE(gemm_shared_a(ar, cur, plan->Vt, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));  // :102, target rows only
     SegParams s;
     seg_from_plan(s, plan);
-    s.D = D; s.table = T; s.stride_idx = (long)L * D; s.stride_type = D;
+    s.D = D;
+    RGNN_PROPAGATE(transform_sources(plan, ar, cur, din, D, edge_weights, T, stream, s));                        // :94 on nodes
+    RGNN_PROPAGATE(gemm_shared_a(ar, cur, plan->Vt, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));  // :102, target rows only
     s.num_incoming = normalize ? num_incoming : nullptr;                      // :96-100
     s.msg_mode = MSG_FILM; s.mod_table = FW; s.mod_stride_node = (long)L * 2 * D; s.mod_stride_type = 2 * D;   // :103-108
     s.act_msg = activation;                                                   // :112 (before the sum)

@@ -10,7 +10,9 @@
 #include "plan.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <new>
+#include <stdlib.h>
 
 namespace rgnn {
 
@@ -93,6 +95,26 @@ __global__ void plan_heavy_kernel(const int32_t* __restrict__ seg_off, int nseg,
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nseg) return;
   if (seg_off[v + 1] - seg_off[v] > threshold) list[atomicAdd(count, 1)] = v;
+}
+
+// ---- compact (source, type) pair table ----
+__global__ void pair_mark_kernel(const int32_t* __restrict__ e_src, const int32_t* __restrict__ e_type, int M, int V,
+                                 int32_t* __restrict__ used) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < M) used[(size_t)e_type[e] * V + e_src[e]] = 1;   // benign race: every writer stores 1
+}
+__global__ void pair_fill_kernel(const int32_t* __restrict__ rank, int V, long VL, int32_t* __restrict__ pair_src) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < VL && rank[i + 1] > rank[i]) pair_src[rank[i]] = (int32_t)(i % V);
+}
+__global__ void pair_edge_kernel(const int32_t* __restrict__ e_src, const int32_t* __restrict__ e_type, int M, int V,
+                                 const int32_t* __restrict__ rank, int32_t* __restrict__ e_pair) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < M) e_pair[e] = rank[(size_t)e_type[e] * V + e_src[e]];
+}
+__global__ void pair_offsets_kernel(const int32_t* __restrict__ rank, int V, int L, int32_t* __restrict__ off) {
+  const int l = threadIdx.x;
+  if (l <= L) off[l] = rank[(size_t)l * V];
 }
 
 void ensure_pool_config(int device) {
@@ -324,6 +346,36 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
     PLAN_CUDA2(cudaGetLastError());
     count_launch();
   }
+  // compact (source, type) pair table for sparsely typed graphs (see plan.cuh)
+  const size_t VL = (size_t)num_nodes * num_edge_types;
+  if ((double)M < 0.75 * (double)VL && getenv("RGNN_NO_PAIRS") == nullptr) {
+    const size_t rank_bytes = align_up(sizeof(int32_t) * (VL + 1), 256);
+    size_t scan_bytes = 0;
+    PLAN_CUDA2(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(VL + 1), stream));
+    scan_bytes = align_up(scan_bytes, 256);
+    PLAN_CUDA2(cudaMallocAsync(&plan->pair_block, 2 * m_bytes + 256, stream));
+    char* pb = static_cast<char*>(plan->pair_block);
+    plan->pair_src = reinterpret_cast<int32_t*>(pb);
+    plan->e_pair = reinterpret_cast<int32_t*>(pb + m_bytes);
+    plan->pair_off_dev = reinterpret_cast<int32_t*>(pb + 2 * m_bytes);
+    char* tmp = nullptr;
+    PLAN_CUDA2(cudaMallocAsync(&tmp, rank_bytes + scan_bytes, stream));
+    int32_t* rank = reinterpret_cast<int32_t*>(tmp);
+    cudaError_t pe = cudaMemsetAsync(rank, 0, sizeof(int32_t) * (VL + 1), stream);
+    if (pe == cudaSuccess) {
+      pair_mark_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(plan->e_src, plan->e_type, (int)M, num_nodes, rank);
+      pe = cub::DeviceScan::ExclusiveSum(tmp + rank_bytes, scan_bytes, rank, rank, (int)(VL + 1), stream);
+    }
+    if (pe == cudaSuccess) {
+      pair_fill_kernel<<<(unsigned)((VL + 255) / 256), 256, 0, stream>>>(rank, num_nodes, (long)VL, plan->pair_src);
+      pair_edge_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(plan->e_src, plan->e_type, (int)M, num_nodes, rank, plan->e_pair);
+      pair_offsets_kernel<<<1, RGNN_MAX_EDGE_TYPES + 1, 0, stream>>>(rank, num_nodes, num_edge_types, plan->pair_off_dev);
+      pe = cudaGetLastError();
+      count_launch(5);
+    }
+    cudaFreeAsync(tmp, stream);
+    PLAN_CUDA2(pe);
+  }
   PLAN_CUDA2(cudaFreeAsync(scratch, stream));
   if (!deferred) {
     const int rc = rgnn_plan_status(plan);
@@ -340,7 +392,16 @@ extern "C" int rgnn_plan_status(const rgnn_plan_t* plan) {
   if (plan->err_flag == nullptr) return RGNN_OK;
   int flags[2] = {0, 0};
   RGNN_CHECK_CUDA(cudaMemcpyAsync(flags, plan->err_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, plan->stream));
+  rgnn_plan* mp = const_cast<rgnn_plan*>(plan);
+  if (plan->pair_off_dev != nullptr && plan->n_pairs < 0)
+    RGNN_CHECK_CUDA(cudaMemcpyAsync(mp->pair_type_off, plan->pair_off_dev, sizeof(int32_t) * (plan->L + 1), cudaMemcpyDeviceToHost, plan->stream));
   RGNN_CHECK_CUDA(cudaStreamSynchronize(plan->stream));
+  if (plan->pair_off_dev != nullptr && plan->n_pairs < 0) {
+    mp->n_pairs = mp->pair_type_off[plan->L];
+    mp->max_type_pairs = 0;
+    for (int l = 0; l < plan->L; ++l)
+      if (mp->pair_type_off[l + 1] - mp->pair_type_off[l] > mp->max_type_pairs) mp->max_type_pairs = mp->pair_type_off[l + 1] - mp->pair_type_off[l];
+  }
   const_cast<rgnn_plan*>(plan)->num_heavy_host = flags[1];
   const int herr = flags[0];
   if (herr != 0) {
@@ -353,6 +414,7 @@ extern "C" int rgnn_plan_status(const rgnn_plan_t* plan) {
 extern "C" int rgnn_plan_destroy(rgnn_plan_t* plan) {
   if (plan == nullptr) return RGNN_OK;
   if (plan->rev_block != nullptr) cudaFreeAsync(plan->rev_block, plan->stream);
+  if (plan->pair_block != nullptr) cudaFreeAsync(plan->pair_block, plan->stream);
   if (plan->block != nullptr) cudaFreeAsync(plan->block, plan->stream);   // stream-ordered: safe after queued forwards
   delete plan;
   return RGNN_OK;

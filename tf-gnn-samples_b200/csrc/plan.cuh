@@ -24,6 +24,17 @@ struct rgnn_plan {
   int32_t* rev_src = nullptr;       // [M]
   int32_t* rev_type = nullptr;      // [M]
   void* rev_block = nullptr;
+  // Compact transform table (sparsely typed graphs): the distinct (source, type) pairs that occur as edges, ordered by
+  // (type, source).  Built at plan creation when M < 0.75 * V * L (then at most that share of the V*L rows of
+  // T = H.[W_0|..|W_{L-1}] is ever gathered): the per-type Dense is applied to these rows only (row-range GEMM whose A rows
+  // follow pair_src) and the edge stage addresses the compact table through e_pair.  QM9-10k: 1.10 of 4 rows per node.
+  int32_t* pair_src = nullptr;      // [n_pairs] source node of compact row r
+  int32_t* e_pair = nullptr;        // [M] compact row of every edge, CSR-by-target order (parallel to e_src / e_type)
+  int32_t* pair_off_dev = nullptr;  // [L+1] device copy of pair_type_off
+  int32_t pair_type_off[RGNN_MAX_EDGE_TYPES + 1] = {0};   // host: rows of type l = [pair_type_off[l], pair_type_off[l+1])
+  int32_t n_pairs = -1;             // host: -1 = no pair table / offsets not read back yet (deferred check)
+  int32_t max_type_pairs = 0;
+  void* pair_block = nullptr;
   // targets with more than RGNN_HEAVY_SEGMENT incoming edges (reduced by a whole CTA, see seg_kernels.cu)
   int32_t* heavy_list = nullptr;    // [V]
   int32_t* rev_heavy_list = nullptr; // [V*L] (reverse index)

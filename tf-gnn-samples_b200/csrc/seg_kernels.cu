@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_kernel(const 
   const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (v >= p.V) return;
   const int col0 = blockIdx.y * (128 * NV) + lane * 4;
-  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);   // plan arrays: not produced by the predecessor kernel
+  pdl_wait();                                                             // the table (T) is: wait for the transform GEMM
+  pdl_launch_dependents();
   if (p.heavy_threshold > 0 && end - beg > p.heavy_threshold) return;   // left to seg_reduce_heavy_kernel
   bool ok[NV];
   float4 acc[NV];
@@ -204,6 +206,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_half_kernel(c
   if (v >= p.V) return;
   const int col0 = blockIdx.y * 64 + l16 * 4;
   const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  pdl_wait();
+  pdl_launch_dependents();
   if (p.heavy_threshold > 0 && end - beg > p.heavy_threshold) return;   // left to seg_reduce_heavy_kernel
   const bool okc = col0 < p.D;
   float4 acc = f4(0.0f);
@@ -647,7 +651,7 @@ static int seg_cols() {   // experiment knob: RGNN_SEG_COLS=256 -> one warp per 
 }
 template <int NV, int MODE, bool MAXAGG, bool SCALED, bool ACTMSG>
 static void launch_seg_pair(const SegParams& p, dim3 grid, cudaStream_t stream) {
-  seg_reduce_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  launch_pdl(seg_reduce_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
   count_launch();
   if (p.heavy_threshold > 0 && p.heavy_known != 0) {   // unknown (-1) or > 0: a few persistent CTAs walk the heavy list
     const unsigned gx = p.heavy_known > 0 ? (unsigned)(p.heavy_known < 592 ? p.heavy_known : 592) : 148u;
@@ -710,8 +714,8 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
     const bool use_half = half_ok && (half_env == 1 || (half_env != 0 && warps128 < 148L * 40));
     if (use_half) {
       const dim3 grid(gx, (p.D + 63) / 64);
-      if (p.num_incoming != nullptr) seg_reduce_half_kernel<true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
-      else seg_reduce_half_kernel<false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+      if (p.num_incoming != nullptr) launch_pdl(seg_reduce_half_kernel<true>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
+      else launch_pdl(seg_reduce_half_kernel<false>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
       count_launch();
       if (p.heavy_threshold > 0 && p.heavy_known != 0) {   // heavy targets: same split kernel as the standard path
         const unsigned hx = p.heavy_known > 0 ? (unsigned)(p.heavy_known < 592 ? p.heavy_known : 592) : 148u;

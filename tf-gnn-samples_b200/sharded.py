@@ -214,7 +214,7 @@ class ShardedGraph:
     def exchange(self, buffer: int):
         """Refresh the halo rows of state buffer ``buffer`` from their owners (rgnn_halo_exchange).  Collective."""
         with torch.cuda.device(self.device):
-            check(load_library().rgnn_halo_exchange(self.handle, int(buffer), self.state_dim, current_stream_ptr(self.device)))
+            check(load_library().rgnn_halo_exchange(self.handle, int(buffer), int(self.state_dim or 0), current_stream_ptr(self.device)))
 
     def halo_bytes(self) -> int:
         return self.n_halo * (self.state_dim or 0) * 4
