@@ -16,8 +16,15 @@ own counter (models/sparse_graph_model.py:285,310: sum of E_l per batch, counted
   roofline     algorithmic bytes of one RGCN layer (M*(4D+12) + V*8D + L*D*D*4) / measured layer
                time, against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
   cpu_baseline the torch-CPU restatement of the reference op order (oracle/ref_torch.py) on this box's cores.
-Multi-GPU: weak scaling, every rank owns its own batch (graphs are independent units: no collective on the
-data path); value = edges of all ranks / max-over-ranks time.
+  value_uncached_weights   the same step with the weight-image cache OFF (pack_b_kernel inside the timed region): what a
+               training step, whose weights change every step, pays.
+  configs      device-timed lines for BASELINE.json configs 3 (GGNN QM9-10k, real molecule structure), 4 (RGAT PPI-shaped,
+               8 heads) and 5 (GNN-FiLM 50k / 1M on one GPU), each with the roofline that bounds it.
+  sharded      (N > 1 only) BASELINE config 5 as ONE graph node-range sharded over the N GPUs through the library's own
+               path (rgnn_halo_plan_create / rgnn_halo_exchange: peer-memory pull over NVLink, no NCCL on the data path):
+               ms per layer, the exchange kernel alone, halo bytes, parity against the reference-generated fixture.
+Multi-GPU headline: weak scaling, every rank owns its own batch (graphs are independent units: no collective on the
+data path); value = edges of all ranks / max-over-ranks time.  The sharded block is the strong-scaling companion.
 """
 import argparse
 import json
@@ -39,6 +46,11 @@ NUM_LINKS = 59000
 METRIC = "edges/sec (device-timed) RGCN PPI hidden=256"
 WORKLOAD = ("RGCN synthetic PPI-shaped batch: V=2245 nodes, M=120245 messages (59000 links fwd+bkwd + self loops), "
             "L=3 edge types, hidden=256, 3 layers, ReLU, sum aggregation with 1/(c+1e-7) normalisation")
+
+
+# the `config` both arms print (identical dicts: the driver compares them); run-specific detail goes under "details"
+CONFIG = {"workload": WORKLOAD, "V": NUM_NODES, "M": 2 * NUM_LINKS + NUM_NODES, "L": 3, "hidden": HIDDEN, "layers": NUM_LAYERS,
+          "activation": "ReLU", "aggregation": "sum", "normalize_by_num_incoming": True, "dtype": "f32", "data": "synthetic (seed 0)"}
 
 
 def algorithmic_bytes_per_layer(V, M, L, D):
@@ -161,8 +173,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference arm = torch-CPU restatement of gnns/rgcn.py op order "
-                   "(TF1 not installable); rank 0 only"},
+        "config": CONFIG,
+        "details": {"note": "reference arm = torch-CPU restatement of gnns/rgcn.py op order (TF1 not installable); rank 0 only"},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -187,6 +199,211 @@ def cpu_baseline(batch, h0, layer_weights, budget_s=12.0):
     return {"value": batch.num_edges / med, "unit": "edges/s", "cores": cores, "kind": "port",
             "sample": "%d full 3-layer forwards over the same batch (median %.1f ms each), torch-CPU restatement of "
                       "gnns/rgcn.py:84-114" % (len(times), med * 1e3)}
+
+
+def load_peaks():
+    """Roofline denominators: the driver-measured numbers of MEASURED_PEAKS.json, else B200_PROFILING.md's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm": float(d["hbm_gbs"]), "bf16": float(d["bf16_tflops"]), "bf16_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "source": "MEASURED_PEAKS.json (measured copy bandwidth / cuBLAS bf16)"}
+    return {"hbm": 6650.0, "bf16": 1650.0, "bf16_sustained": 1400.0, "source": "fallback of B200_PROFILING.md"}
+
+
+def time_graph(fn, dev, flush, n=20, warmup=3):
+    """Record `fn` (public API calls) once into a CUDA graph and return the median device time (ms) of n replays, L2
+    flushed before each (untimed).  The graph removes host launch latency from short layers; the kernels are the same."""
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = fn()
+    ts = []
+    for i in range(warmup + n):
+        flush.zero_()
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        g.replay()
+        en.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ts.append(st.elapsed_time(en))
+    del keep
+    return statistics.median(ts)
+
+
+def extra_configs(dev, flush, peaks):
+    """BASELINE.json configs 3, 4, 5 on one GPU: one line each (device-timed CUDA-graph replay of ONE layer call, cold L2).
+    Parity of these exact configurations against the reference-generated fixtures is tests/test_reference_pin.py (-m gpu)."""
+    import numpy as np
+    import torch
+    import tf_gnn_samples_b200 as G
+    from tf_gnn_samples_b200 import batching, weights as W
+    hbm = peaks["hbm"]
+    tensor_peak = peaks["bf16_sustained"] / 2.0 / 3.0        # TF32 rate = bf16 / 2; fp32-accurate products need 3 TF32 passes
+    lines = []
+
+    def states(V, D):
+        return torch.as_tensor(np.tanh(np.random.default_rng(1).standard_normal((V, D))).astype(np.float32)).to(dev)
+
+    # ---- config 3: GGNN, the real 10,000 QM9 validation molecules (4 bond types), hidden 128, GRU, 4 timesteps ----
+    struct = os.path.join(ROOT, "tests", "golden", "qm9_valid_structure.npz")
+    b, _, _ = batching.qm9_batch(batching.qm9_records_from_structure(struct), add_self_loop_edges=False)
+    V, M, L, D, T = b.num_nodes, b.num_edges, len(b.adjacency_lists), 128, 4
+    h = states(V, D)
+    plan = G.GraphPlan(b.adjacency_lists, V, device=dev)
+    w = W.to_torch(W.ggnn_weights(L, D), dev)
+    ms = time_graph(lambda: G.sparse_ggnn_layer(h, plan, D, num_timesteps=T, weights=w), dev, flush)
+    flops = T * (V * L * D * D * 2 + V * (2 * D) * (3 * D) * 2)          # SURVEY 8d: 59 GF per timestep
+    lines.append({"config": "config 3: GGNN QM9 10k graphs (real validation molecules: V=%d M=%d L=%d) hidden=128 GRU %d timesteps, 1xB200" % (V, M, L, T),
+                  "ms_per_call": ms, "ms_per_timestep": ms / T, "edges_per_s": M / (ms * 1e-3),
+                  "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                               "frac": flops / (ms * 1e-3) / 1e12 / tensor_peak,
+                               "what": "algorithmic fp32 FLOPs (SURVEY.md 8d: per timestep V*L*D^2*2 for the per-type transforms + V*2D*3D*2 for the GRU) / time, "
+                                       "against the fp32-accurate tensor peak = measured sustained bf16 / 2 (TF32 rate) / 3 (3xTF32 split products)",
+                               "hbm_frac_of_algorithmic_bytes": T * (M * (4 * D + 8) + V * 8 * D + L * D * D * 4) / (ms * 1e-3) / 1e9 / hbm}})
+    plan.close()
+    # ---- config 4: RGAT on the PPI-shaped batch, hidden 256, 8 heads ----
+    b = batching.ppi_like_batch()
+    V, M, L, D, K = b.num_nodes, b.num_edges, len(b.adjacency_lists), 256, 8
+    h = states(V, D)
+    plan = G.GraphPlan(b.adjacency_lists, V, device=dev)
+    w = W.to_torch(W.rgat_weights(L, D, D), dev)
+    ms = time_graph(lambda: G.sparse_rgat_layer(h, plan, D, num_heads=K, activation_function="tanh", weights=w), dev, flush)
+    alg = M * (4 * D + 8 + 4 * K) + V * 8 * D + L * D * D * 4
+    lines.append({"config": "config 4: RGAT PPI-shaped (V=%d M=%d L=%d) hidden=256 8 heads, 1xB200" % (V, M, L), "ms_per_call": ms,
+                  "edges_per_s": M / (ms * 1e-3),
+                  "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm,
+                               "what": "algorithmic bytes M*(4D + 8 + 4K) + V*8D + L*D^2*4 (SURVEY.md 8d) / time"}})
+    plan.close()
+    # ---- config 5 on ONE GPU: GNN-FiLM, VarMisuse-shaped random graph V=50k M=1M L=6, hidden 128 ----
+    b = batching.varmisuse_like_batch()
+    V, M, L, D = b.num_nodes, b.num_edges, len(b.adjacency_lists), 128
+    h = states(V, D)
+    cnt = torch.as_tensor(b.type_to_num_incoming_edges).to(dev)
+    plan = G.GraphPlan(b.adjacency_lists, V, device=dev)
+    w = W.to_torch(W.film_weights(L, D, D), dev)
+    ms = time_graph(lambda: G.sparse_gnn_film_layer(h, plan, cnt, D, weights=w), dev, flush)
+    alg = M * (4 * D + 8) + V * 8 * D + L * D * D * 4 + V * L * 8 * D
+    flops = V * L * D * D * 2 * 3                                          # W_l h (D) + F_l h (2D) per (node, type)
+    lines.append({"config": "config 5 on one GPU: GNN-FiLM VarMisuse-shaped random graph (V=%d M=%d L=%d) hidden=128, 1xB200" % (V, M, L),
+                  "ms_per_call": ms, "edges_per_s": M / (ms * 1e-3),
+                  "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm,
+                               "what": "algorithmic bytes M*(4D + 8) + V*8D + L*D^2*4 + gamma/beta rows V*L*8D (SURVEY.md 8d) / time",
+                               "tensor_frac_of_algorithmic_flops": flops / (ms * 1e-3) / 1e12 / tensor_peak}})
+    plan.close()
+    return lines
+
+
+def sharded_block(dev, rank, world, local_rank, flush, peaks, layers=4, iters=30):
+    """BASELINE config 5 as ONE graph over `world` GPUs through librgnn's sharded path: node-range partition built on the
+    device, halo rows pulled out of the owners' peer-mapped state buffers by one kernel per layer (device-side barrier
+    inside), FiLM layers writing their owned rows straight into the next layer's peer-visible buffer; the K-layer
+    sequence is one CUDA graph per rank.  Time = max over ranks (CUDA events)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import tf_gnn_samples_b200 as G
+    from tf_gnn_samples_b200 import batching, weights as W
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_cases as RC
+    D = 128
+    out = {"what": "GNN-FiLM VarMisuse-shaped V=50k M=1M L=6 hidden=128 (BASELINE config 5), ONE graph node-range sharded over %d GPUs "
+                   "(strong scaling); exchange = rgnn_halo_exchange: one pull kernel per layer over CUDA-IPC peer memory (NVLink), "
+                   "cross-rank barrier inside the kernel; no NCCL call on the data path" % world,
+           "limiting_step": "halo_pull_kernel (peer reads over NVLink) + the per-rank source transform, which covers every local row "
+                            "(owned + halo) unless the compact (source, type) table applies", "variants": []}
+
+    def barrier():
+        dist.barrier(device_ids=[local_rank])
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for packed, fixture in ((0, "config5_film_random"), (25, "config5_film_packed")):
+        b = batching.varmisuse_like_batch(packed_graphs=packed, seed=0)
+        h_all = np.tanh(np.random.default_rng(1).standard_normal((b.num_nodes, D))).astype(np.float32)
+        ws = [W.to_torch(W.film_weights(len(b.adjacency_lists), D, D, seed=2 + 10 * i), dev) for i in range(layers)]
+        cuts = G.degree_balanced_cuts(b.adjacency_lists, b.num_nodes, world)
+        sg = G.ShardedGraph(b.adjacency_lists, cuts, rank, world, device=dev)
+        sg.attach(D)
+        cnt = sg.local_num_incoming(b.type_to_num_incoming_edges)
+        h_own = torch.as_tensor(h_all[sg.lo:sg.hi]).to(dev)
+
+        def stack(k):
+            for t in range(k):
+                sg.exchange(t % 2)
+                G.sparse_gnn_film_layer(sg.states(t % 2), sg.plan, cnt, D, weights=ws[t], out=sg.states(1 - t % 2))
+
+        # parity of ONE sharded layer (weights of layer 0 = the fixture's) against the reference-generated fixture
+        sg.states(0)[: sg.n_own] = h_own
+        torch.cuda.synchronize(); barrier()
+        stack(1)
+        torch.cuda.synchronize(); barrier()
+        mine = sg.states(1)[: sg.n_own].contiguous()
+        sizes = [None] * world
+        dist.all_gather_object(sizes, int(mine.shape[0]))
+        parts = [torch.empty((n, D), device=dev) for n in sizes]
+        dist.all_gather(parts, mine)
+        parity = None
+        if rank == 0:
+            z = np.load(RC.fixture_path(fixture))
+            er, ep, ec = RC.compare_with_summary(torch.cat(parts).cpu().numpy(), z)
+            parity = {"max_norm_rel_err_rows": er, "projection": ep, "column_sums": ec, "reference_float32_path": float(z["err32"]),
+                      "against": "tests/golden/ref_%s.npz = the reference's gnn_film.py executed through tests/tf1_shim (float64)" % fixture,
+                      "ok": bool(max(er, ep, ec) <= 1e-4)}
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(); barrier()
+            st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            st.record()
+            for _ in range(n):
+                fn()
+            en.record()
+            torch.cuda.synchronize(); barrier()
+            return maxr(st.elapsed_time(en) / n)
+
+        K = layers - layers % 2                       # even: the step ends in buffer 0 again and can be replayed
+        eager_ms = timed(lambda: stack(K), iters) / K
+        exch_ms = timed(lambda: (sg.exchange(0), sg.exchange(1)), iters) / 2
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            stack(K)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(); barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            stack(K)
+        torch.cuda.synchronize(); barrier()
+        graph_ms = timed(graph.replay, iters) / K
+        halo = torch.tensor([sg.n_halo, sg.n_local, sg.plan.num_edges], dtype=torch.int64, device=dev)
+        dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+        hb = int(halo[0]) * D * 4
+        if rank == 0:
+            out["variants"].append({
+                "graph": "packed %d graphs of 2,000 nodes (block-diagonal)" % packed if packed else "one random graph (worst-case halo)",
+                "ms_per_layer": graph_ms, "ms_per_layer_eager_api": eager_ms, "ms_exchange_kernel": exch_ms,
+                "edges_per_s": b.num_edges / (graph_ms * 1e-3), "layers_per_step": K,
+                "max_halo_rows_per_rank": int(halo[0]), "max_local_rows_per_rank": int(halo[1]), "max_local_edges_per_rank": int(halo[2]),
+                "halo_bytes_per_rank_per_layer": hb, "exchange_GBps_per_rank": hb / (exch_ms * 1e-3) / 1e9 if hb else None,
+                "parity_vs_reference_one_layer": parity})
+        sg.close()
+        barrier()
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -307,6 +524,27 @@ def run_ours(args, rank, world, local_rank):
         e.record()
         torch.cuda.synchronize()
         warm_ms = s.elapsed_time(e) / args.steps
+    # the same 3-layer step with the weight-image cache OFF: pack_b_kernel runs inside the timed region (a training step,
+    # whose weights change every step, pays this)
+    G.set_weight_cache(False)
+    forward(h_dev)
+    torch.cuda.synchronize()
+    n1 = launch_count()
+    forward(h_dev)
+    kernels_uncached = launch_count() - n1
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        forward(h_dev)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph_uncached = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph_uncached):
+        out_uncached = forward(h_dev)
+    graph_uncached.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out_uncached, out_eager), "uncached-weights step differs from the cached one"
+    uncached_total_ms, _ = timed_steps(graph_uncached.replay, args.steps, args.warmup)
+    G.set_weight_cache(True)
     clocks = sampler.stop() if sampler else None
 
     total_ms = max_over_ranks(total_ms)
@@ -315,6 +553,7 @@ def run_ours(args, rank, world, local_rank):
     value = edges_all / (ms_per_step * 1e-3)
     layer_ms = max_over_ranks(layer_total_ms) / args.steps
     layer_api_ms = max_over_ranks(layer_api_ms) / args.steps
+    uncached_ms = max_over_ranks(uncached_total_ms) / args.steps
 
     # ---------------- e2e: host buffers -> public API -> host ----------------
     if args.skip_e2e:
@@ -423,38 +662,55 @@ def run_ours(args, rank, world, local_rank):
     except Exception as exc:   # keep the eager number if anything about capture is unsupported on this box
         print("e2e graph capture unavailable: %r" % (exc,), file=sys.stderr)
         e2e_graph_s = None
-    e2e_s = e2e_graph_s if e2e_graph_s is not None else e2e_eager_s
-    e2e_value = edges_all / (e2e_s / args.steps)
+    # headline e2e = the eager public-API calls a user makes every step; the graph replay of the same calls is reported beside it
+    e2e_value = edges_all / (e2e_eager_s / args.steps)
+    e2e_graph_value = edges_all / (e2e_graph_s / args.steps) if e2e_graph_s is not None else None
+
+    peaks = load_peaks()
+    configs = extra_configs(dev, flush, peaks) if (world == 1 and not args.skip_configs) else None   # the N=1 run carries them
+    if world > 1:
+        barrier()
+    sharded = None
+    if world > 1 and not args.skip_sharded:
+        try:
+            sharded = sharded_block(dev, rank, world, local_rank, flush, peaks)
+        except Exception as exc:   # keep the headline line if peer memory is unavailable on this box
+            sharded = {"unavailable": repr(exc)}
+            print("sharded block failed on rank %d: %r" % (rank, exc), file=sys.stderr)
 
     if rank != 0:
         return
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        with open(peaks_path) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    peak, peak_src = peaks["hbm"], peaks["source"]
     layer_bytes = algorithmic_bytes_per_layer(V, M, L, HIDDEN)
     # one "launch" = one layer (transform GEMM + edge-stage kernel): its average duration over the timed region is the
     # step time / layers (cold L2 for the first layer of every step, the later layers start from what the previous one left)
     layer_in_step_ms = ms_per_step / NUM_LAYERS
     achieved = layer_bytes / (layer_in_step_ms * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_layer")
+    traffic_src = None
+    for name in ("r02_traffic.json", "r01_traffic.json"):      # written from the round's own ncu --set full capture (tools/ncu_traffic.py)
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_layer")
+            traffic_src = "profiles/" + name
+            break
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "step": "3 x sparse_rgcn_layer replayed as one CUDA graph (%d kernels)" % kernels_per_step,
-                   "parallelism": "independent batch per rank (graph-boundary sharding, no collective)",
-                   "weights": "static: packed TF32 hi/lo weight images cached across steps (rgnn_set_weight_cache)",
-                   "warm_l2_ms_per_step": warm_ms, "per_layer_edges_per_s": M / (layer_ms * 1e-3)},
+        "config": CONFIG,
+        "details": {"l2": "flushed between timed steps (256 MiB write, untimed)",
+                    "step": "3 x sparse_rgcn_layer replayed as one CUDA graph (%d kernels, programmatic dependent launches)" % kernels_per_step,
+                    "parallelism": "independent batch per rank (graph-boundary sharding, no collective); see 'sharded' for the node-range-sharded single graph",
+                    "weights": "value: static weights, packed TF32 hi/lo weight images cached across steps (rgnn_set_weight_cache); "
+                               "value_uncached_weights: cache off, pack_b_kernel inside the timed region",
+                    "warm_l2_ms_per_step": warm_ms, "per_layer_edges_per_s": M / (layer_ms * 1e-3)},
+        "value_uncached_weights": {"value": edges_all / (uncached_ms * 1e-3), "unit": "edges/s", "ms_per_step": uncached_ms,
+                                   "kernels_per_step": int(kernels_uncached),
+                                   "roofline_frac": layer_bytes / (uncached_ms / NUM_LAYERS * 1e-3) / 1e9 / peak},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "one RGCN layer = gemm_tcgen05_kernel (node transform, tcgen05 3xTF32) + seg_reduce_kernel (fused edge stage)",
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "one RGCN layer = gemm_tcgen05_kernel (node transform, tcgen05 3xTF32) + seg_reduce_kernel (fused edge stage)",
                      "algorithmic_bytes_per_launch": layer_bytes, "ms_per_launch": layer_in_step_ms,
                      "ms_per_launch_what": "timed region / (steps x layers): average duration of one layer inside the step",
                      "ms_single_layer_cold_l2": layer_ms, "frac_single_layer_cold_l2": layer_bytes / (layer_ms * 1e-3) / 1e9 / peak,
@@ -463,13 +719,19 @@ def run_ours(args, rank, world, local_rank):
                              "compares algorithmic bytes with the HBM copy peak; the binding resource is L2->SM delivery "
                              "(165 MB per layer at ~7 TB/s), see DESIGN.md 5.3 and profiles/r01_final_kernels.txt"},
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s / args.steps * 1e3, "mode": e2e_mode,
-                "eager_ms_per_step": e2e_eager_s / args.steps * 1e3,
+                "ms_per_step": e2e_eager_s / args.steps * 1e3, "mode": "eager public-API calls every step (GraphPlan + rgcn_layer_stack)",
+                "graph_replay_value": e2e_graph_value,
+                "graph_replay_ms_per_step": e2e_graph_s / args.steps * 1e3 if e2e_graph_s is not None else None,
+                "graph_replay_mode": e2e_mode,
                 "what": "pinned host adjacency+in-degrees H2D -> GraphPlan build (overlapping the H2D of the node features) -> rgcn_layer_stack (3 layers) "
                         "-> D2H of final node states -> sync -> index-range check"},
         "gpu_launches": int(kernels_per_step * args.steps),
         "clocks": clocks,
     }
+    if configs is not None:
+        line["configs"] = configs
+    if sharded is not None:
+        line["sharded"] = sharded
     if world == 1 and not args.skip_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(batch, h0, layer_weights)
     emit(line)
@@ -494,6 +756,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs: leave out the CPU leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: leave out the host-buffer leg")
+    ap.add_argument("--skip-configs", action="store_true", help="leave out the lines for BASELINE configs 3-5")
+    ap.add_argument("--skip-sharded", action="store_true", help="N > 1: leave out the node-range-sharded config-5 block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

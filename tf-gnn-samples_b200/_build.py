@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "librgnn.so")
+LIB_PATH = os.environ.get("RGNN_LIB_PATH") or os.path.join(LIB_DIR, "librgnn.so")   # RGNN_LIB_PATH: measurement variants (build_variant)
 STAMP = os.path.join(LIB_DIR, "librgnn.stamp")
 SOURCES = ["gemm_tcgen05.cu", "gemm_tn_tcgen05.cu", "plan.cu", "halo.cu", "seg_kernels.cu", "layers.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -30,7 +30,10 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                    // fp32 elements per 128-byte swizzle row
-constexpr int TC_GROUPS = 2;                 // producer groups alternate K chunks (see the producer loop)
+#ifndef RGNN_TC_GROUPS
+#define RGNN_TC_GROUPS 2
+#endif
+constexpr int TC_GROUPS = RGNN_TC_GROUPS;    // producer groups take K chunks round-robin (see the producer loop): bytes of A in flight per CTA = TC_GROUPS x 16 KB
 constexpr int TC_GROUP_WARPS = 4;            // one group covers the 128-row tile: 4 warps x 32 rows of TMEM lanes
 constexpr int TC_PRODUCER_WARPS = TC_GROUPS * TC_GROUP_WARPS;
 constexpr int TC_GROUP_THREADS = 32 * TC_GROUP_WARPS;
@@ -230,7 +233,10 @@ __device__ __forceinline__ void epilogue_blocks(const TcParams& p, const TileInf
 // CL = thread-block cluster size (1, 2 or 4).  The CL CTAs of a cluster work on CL consecutive m-tiles of the SAME
 // n-tile in lock step; each loads 1/CL of every weight-image chunk and TMA-multicasts it to all of them, so the
 // L2->SM traffic of B (the bound of this kernel, profiles/r01_gemm_tcgen05_timeline.txt) drops by CL.
-template <int EPI, int CL>
+// GATHER: A rows follow an index list (GemmParams::a_rows: the compact (source, type) transform).  A separate instance,
+// so that the common kernel stays under the ~2048-instruction L1.5 I-cache (the 16 extra index loads + selects of the
+// gathered form pushed every variant over it: 86.9 -> 107 us on the headline step, gpurun_out r02 job B).
+template <int EPI, int CL, bool GATHER = false>
 __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const GemmParams& g = p.g;
@@ -302,9 +308,14 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
         const int f = ptid + i * TC_GROUP_THREADS;
         const int row = f >> 3, c16 = f & 7;
         const int grow = ti.m0 + row, gk = k0 + c16 * 4;
-        const bool in = grow < ti.row_end && gk < Kseg;
-        const int arow = (in && g.a_rows != nullptr && !seg2) ? __ldg(g.a_rows + grow) : grow;   // gathered A (index list hits L1 after the first chunk)
-        v[i] = in ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)arow * lda + gk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (GATHER) {
+          const bool in = grow < ti.row_end && gk < Kseg;
+          const int arow = in ? __ldg(g.a_rows + grow) : 0;   // the index list hits L1 after the tile's first chunk
+          v[i] = in ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)arow * lda + gk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          v[i] = (grow < ti.row_end && gk < Kseg) ? __ldg(reinterpret_cast<const float4*>(Abase + (size_t)grow * lda + gk))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     float4 va[8];
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
       const bool last = (it == my_tiles - 1);
       if (lane == 0 && warp == 0 && it == 0) TC_TRACE(50);
       if (lane == 0 && warp == PROD_WARP0) TC_TRACE(52);
-      epilogue_blocks<EPI>(p, ti, lane_base, stage_q, quarter, lane, last ? cb_last : 0, last ? 3 * EPI_COLS : EPI_COLS);
+      epilogue_blocks<EPI>(p, ti, lane_base, stage_q, quarter, lane, last ? cb_last : 0, last ? (TC_GROUPS + 1) * EPI_COLS : EPI_COLS);
       if (lane == 0 && warp == 0 && it == 0) TC_TRACE(51);
       if (lane == 0 && warp == PROD_WARP0) TC_TRACE(53);
       tc_fence_before_sync();
@@ -637,10 +648,15 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
     }
   };
   KernelFn fn = pick(g.epi);
-  static bool attr_done[MAX_DEV][3][5] = {};
-  if (!attr_done[dv][g.epi][CL]) {
+  if (g.a_rows != nullptr) {
+    RGNN_REQUIRE(g.epi == EPI_STORE && CL == 1 && g.K2 == 0, "gemm: gathered A rows support the plain store epilogue, one K segment, no cluster");
+    fn = gemm_tcgen05_kernel<EPI_STORE, 1, true>;
+  }
+  static bool attr_done[MAX_DEV][4][5] = {};
+  const int attr_slot = g.a_rows != nullptr ? 3 : g.epi;
+  if (!attr_done[dv][attr_slot][CL]) {
     RGNN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
-    attr_done[dv][g.epi][CL] = true;
+    attr_done[dv][attr_slot][CL] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(TC_THREADS_V4);
