@@ -129,9 +129,22 @@ int transform_sources(const rgnn_plan_t* plan, Arena& ar, const float* cur, int 
   return RGNN_OK;
 }
 
+// scratch for the multi-CTA split of heavy targets (seg_kernels.cu); nothing when the plan is known to have none
+size_t heavy_scratch_floats(const rgnn_plan_t* plan, size_t d) {
+  return plan->num_heavy_host == 0 ? 0 : (size_t)plan->heavy_items_cap * d;
+}
+void seg_heavy_scratch(SegParams& s, const rgnn_plan_t* plan, Arena& ar, int d) {
+  if (plan->num_heavy_host == 0 || plan->heavy_items == nullptr) return;
+  float* scratch = ar.floats((size_t)plan->heavy_items_cap * d);
+  if (ar.overflow) return;   // the caller's check_ws reports it
+  s.heavy_scratch = scratch;
+}
+
 void seg_from_plan(SegParams& s, const rgnn_plan_t* plan) {
   s.V = plan->Vt; s.L = plan->L; s.scale_ld = plan->V;   // only the wanted target rows are reduced (rgnn_plan_set_num_targets)
   s.heavy_list = plan->heavy_list; s.heavy_count = plan->err_flag + 1;
+  s.heavy_base = plan->heavy_base; s.heavy_items = plan->heavy_items; s.heavy_item_count = plan->err_flag + 3;
+  s.heavy_items_known = plan->num_heavy_items_host; s.heavy_items_cap = plan->heavy_items_cap; s.heavy_chunk = RGNN_HEAVY_CHUNK;
   s.heavy_threshold = RGNN_HEAVY_SEGMENT; s.heavy_known = plan->num_heavy_host;
   s.seg_off = plan->seg_off; s.e_type = plan->e_type; s.e_idx = plan->e_src;
 }
@@ -296,6 +309,7 @@ extern "C" size_t rgnn_workspace_bytes(const rgnn_plan_t* plan, int layer_kind, 
   }
   // scratch for the pre-swizzled hi/lo weight images of the largest dense contraction of the layer
   const size_t pack = 2 * (2 * dm + 64) * (2 * L * dm + 2 * dm + 512);
+  floats += heavy_scratch_floats(plan, dm) + 64;   // partial rows of split heavy targets
   return (floats + pack) * sizeof(float) + pad;
 }
 
@@ -320,6 +334,8 @@ extern "C" int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* h, int32_
   float* T = ar.floats((size_t)V * nb * d_out);
   float* buf[2] = {nullptr, nullptr};
   if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * d_out); buf[1] = ar.floats((size_t)V * d_out); }
+  SegParams heavy;
+  seg_heavy_scratch(heavy, plan, ar, d_out);
   RGNN_PROPAGATE(check_ws(ar, "rgcn"));
 
   const float* bp[RGNN_MAX_EDGE_TYPES];
@@ -343,7 +359,7 @@ extern "C" int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* h, int32_
     s.num_incoming = normalize ? num_incoming : nullptr;                      // rgcn.py:100-104
     if (both) { s.msg_mode = MSG_ADDTGT; s.mod_table = T + (size_t)L * d_out; s.mod_stride_node = (long)nb * d_out; s.mod_stride_type = d_out; }
     s.agg = aggregation; s.act_out = activation;                              // rgcn.py:110,114
-    s.out = dst; s.ld_out = d_out;
+    s.out = dst; s.ld_out = d_out; s.heavy_scratch = heavy.heavy_scratch;
     RGNN_PROPAGATE(launch_seg_reduce(s, stream));
     cur = dst; din = d_out;
   }
@@ -533,6 +549,8 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
   float* z = ar.floats((size_t)V * D);
   float* rh = ar.floats((size_t)V * D);
   float* buf[2] = {ar.floats((size_t)V * D), ar.floats((size_t)V * D)};
+  SegParams heavy;
+  seg_heavy_scratch(heavy, plan, ar, D);
   RGNN_PROPAGATE(check_ws(ar, "ggnn"));
 
   const float* cur = h;
@@ -542,7 +560,7 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
     seg_from_plan(s, plan);
     s.D = D;
     RGNN_PROPAGATE(transform_sources(plan, ar, cur, D, D, edge_weights, T, stream, s));   // ggnn.py:80-82
-    s.agg = aggregation; s.out = m; s.ld_out = D;                             // ggnn.py:87-90
+    s.agg = aggregation; s.out = m; s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;   // ggnn.py:87-90
     RGNN_PROPAGATE(launch_seg_reduce(s, stream));
     GemmParams g;
     g.A1 = m; g.lda1 = D; g.K1 = D;
@@ -635,6 +653,8 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
   float* FW = ar.floats((size_t)V * L * 2 * D);
   float* buf[2] = {nullptr, nullptr};
   if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * D); buf[1] = ar.floats((size_t)V * D); }
+  SegParams heavy;
+  seg_heavy_scratch(heavy, plan, ar, D);
   RGNN_PROPAGATE(check_ws(ar, "gnn_film"));
 
   const float* cur = h;
@@ -651,7 +671,7 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
     s.act_msg = activation;                                                   // :112 (before the sum)
     s.agg = aggregation;                                                      // :113-116
     s.ln_gamma = ln_gamma + (size_t)t * D; s.ln_beta = ln_beta + (size_t)t * D;   // :120
-    s.out = dst; s.ld_out = D;
+    s.out = dst; s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;
     RGNN_PROPAGATE(launch_seg_reduce(s, stream));
     cur = dst; din = D;
   }

@@ -117,6 +117,23 @@ __global__ void pair_offsets_kernel(const int32_t* __restrict__ rank, int V, int
   if (l <= L) off[l] = rank[(size_t)l * V];
 }
 
+// forward plan: heavy targets AND their work items (RGNN_HEAVY_CHUNK edges each) for the multi-CTA split
+__global__ void plan_heavy_split_kernel(const int32_t* __restrict__ seg_off, int nseg, int threshold, int chunk,
+                                        int32_t* __restrict__ list, int32_t* __restrict__ base_of, int2* __restrict__ items,
+                                        int items_cap, int* __restrict__ count, int* __restrict__ item_count) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nseg) return;
+  const int deg = seg_off[v + 1] - seg_off[v];
+  if (deg <= threshold) return;
+  const int n = (deg + chunk - 1) / chunk;
+  const int base = atomicAdd(item_count, n);
+  const int i = atomicAdd(count, 1);
+  list[i] = v;
+  base_of[i] = base;
+  for (int c = 0; c < n; ++c)
+    if (base + c < items_cap) items[base + c] = make_int2(v, c);
+}
+
 void ensure_pool_config(int device) {
   static bool done[64] = {false};
   if (device < 0 || device >= 64 || done[device]) return;
@@ -269,7 +286,9 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
   const size_t off_bytes = align_up(sizeof(int32_t) * ((size_t)num_nodes + 1), 256);
   const size_t m_bytes = align_up(sizeof(int32_t) * Mz, 256);
   plan->stream = stream;
-  PLAN_CUDA(cudaMallocAsync(&plan->block, off_bytes + 5 * m_bytes + 256 + off_bytes, stream));
+  plan->heavy_items_cap = (int32_t)(3 * Mz / (2 * RGNN_HEAVY_CHUNK) + 2);
+  const size_t items_bytes = align_up(sizeof(int2) * (size_t)plan->heavy_items_cap, 256);
+  PLAN_CUDA(cudaMallocAsync(&plan->block, off_bytes + 5 * m_bytes + 256 + 2 * off_bytes + items_bytes, stream));
   {
     char* b = static_cast<char*>(plan->block);
     plan->seg_off = reinterpret_cast<int32_t*>(b);
@@ -280,12 +299,15 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
     plan->o_tgt = reinterpret_cast<int32_t*>(b + off_bytes + 4 * m_bytes);
     plan->err_flag = reinterpret_cast<int*>(b + off_bytes + 5 * m_bytes);
     plan->heavy_list = reinterpret_cast<int32_t*>(b + off_bytes + 5 * m_bytes + 256);
+    plan->heavy_base = reinterpret_cast<int32_t*>(b + off_bytes + 5 * m_bytes + 256 + off_bytes);
+    plan->heavy_items = reinterpret_cast<int32_t*>(b + off_bytes + 5 * m_bytes + 256 + 2 * off_bytes);
   }
   PLAN_CUDA(cudaMemsetAsync(plan->err_flag, 0, 4 * sizeof(int), stream));
 
   if (M == 0) {
     PLAN_CUDA(cudaMemsetAsync(plan->seg_off, 0, sizeof(int32_t) * ((size_t)num_nodes + 1), stream));
     plan->num_heavy_host = 0;
+    plan->num_heavy_items_host = 0;
     if (!deferred) PLAN_CUDA(cudaStreamSynchronize(stream));
     *out = plan;
     return RGNN_OK;
@@ -341,8 +363,10 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
     count_launch();
   }
   if (num_nodes > 0) {
-    plan_heavy_kernel<<<(num_nodes + 255) / 256, 256, 0, stream>>>(plan->seg_off, num_nodes, RGNN_HEAVY_SEGMENT, plan->heavy_list,
-                                                                  plan->err_flag + 1);
+    plan_heavy_split_kernel<<<(num_nodes + 255) / 256, 256, 0, stream>>>(plan->seg_off, num_nodes, RGNN_HEAVY_SEGMENT, RGNN_HEAVY_CHUNK,
+                                                                        plan->heavy_list, plan->heavy_base,
+                                                                        reinterpret_cast<int2*>(plan->heavy_items), plan->heavy_items_cap,
+                                                                        plan->err_flag + 1, plan->err_flag + 3);
     PLAN_CUDA2(cudaGetLastError());
     count_launch();
   }
@@ -390,8 +414,8 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
 extern "C" int rgnn_plan_status(const rgnn_plan_t* plan) {
   RGNN_REQUIRE(plan != nullptr, "plan_status: plan is NULL");
   if (plan->err_flag == nullptr) return RGNN_OK;
-  int flags[2] = {0, 0};
-  RGNN_CHECK_CUDA(cudaMemcpyAsync(flags, plan->err_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, plan->stream));
+  int flags[4] = {0, 0, 0, 0};
+  RGNN_CHECK_CUDA(cudaMemcpyAsync(flags, plan->err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, plan->stream));
   rgnn_plan* mp = const_cast<rgnn_plan*>(plan);
   if (plan->pair_off_dev != nullptr && plan->n_pairs < 0)
     RGNN_CHECK_CUDA(cudaMemcpyAsync(mp->pair_type_off, plan->pair_off_dev, sizeof(int32_t) * (plan->L + 1), cudaMemcpyDeviceToHost, plan->stream));
@@ -403,6 +427,7 @@ extern "C" int rgnn_plan_status(const rgnn_plan_t* plan) {
       if (mp->pair_type_off[l + 1] - mp->pair_type_off[l] > mp->max_type_pairs) mp->max_type_pairs = mp->pair_type_off[l + 1] - mp->pair_type_off[l];
   }
   const_cast<rgnn_plan*>(plan)->num_heavy_host = flags[1];
+  const_cast<rgnn_plan*>(plan)->num_heavy_items_host = flags[3];
   const int herr = flags[0];
   if (herr != 0) {
     set_error("plan: adjacency list holds a node index outside [0, %d)", plan->V);

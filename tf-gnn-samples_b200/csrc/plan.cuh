@@ -38,6 +38,12 @@ struct rgnn_plan {
   // targets with more than RGNN_HEAVY_SEGMENT incoming edges (reduced by a whole CTA, see seg_kernels.cu)
   int32_t* heavy_list = nullptr;    // [V]
   int32_t* rev_heavy_list = nullptr; // [V*L] (reverse index)
+  // multi-CTA split of the heavy targets: target i of heavy_list owns the work items [heavy_base[i], heavy_base[i] + n_i),
+  // item j = the j-th RGNN_HEAVY_CHUNK edges of the target's segment; heavy_items[k] = (target, chunk) of item k
+  int32_t* heavy_base = nullptr;    // [V] first item of heavy target i
+  int32_t* heavy_items = nullptr;   // [2 * heavy_items_cap] (target, chunk) pairs
+  int32_t heavy_items_cap = 0;      // upper bound of the item count (3 M / 512 + 2)
+  int num_heavy_items_host = -1;    // host copy of flags[3] once rgnn_plan_status has read it
   int num_heavy_host = -1;          // host copy of flags[1] once rgnn_plan_status has read it, else -1
   int* err_flag = nullptr;          // device flags: [0] out-of-range node id seen, [1] number of heavy targets, [2] heavy (source,type) pairs      // device flag: an adjacency list held an out-of-range node id
   void* block = nullptr;        // the one pool allocation behind all arrays above
@@ -48,4 +54,5 @@ namespace rgnn {
 // Build plan->rev_* on `stream` if absent (not thread-safe; called by the first backward on this plan).
 int plan_ensure_reverse(rgnn_plan* plan, cudaStream_t stream);
 constexpr int RGNN_HEAVY_SEGMENT = 512;
+constexpr int RGNN_HEAVY_CHUNK = 256;     // edges per work item of a split heavy target (one CTA each)
 }  // namespace rgnn

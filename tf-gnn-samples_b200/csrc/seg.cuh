@@ -37,6 +37,13 @@ struct SegParams {
   const int* heavy_count = nullptr;    // device counter
   int heavy_threshold = 0;             // 0 = no splitting
   int heavy_known = -1;                // host copy of *heavy_count, or -1 when it was never read back
+  // multi-CTA split (forward plans; needs scratch): every RGNN_HEAVY_CHUNK edges of a heavy target are one work item reduced
+  // by one CTA into heavy_scratch[item, :]; a second kernel adds a target's partial rows in a fixed order and finishes the row
+  const int32_t* heavy_base = nullptr; // [heavy targets] first item of heavy target i
+  const int32_t* heavy_items = nullptr;// (target, chunk) pairs
+  const int* heavy_item_count = nullptr;
+  int heavy_items_known = -1, heavy_items_cap = 0, heavy_chunk = 0;
+  float* heavy_scratch = nullptr;      // [heavy_items_cap, D] floats; NULL -> one CTA per heavy target (no split)
 };
 int launch_seg_reduce(const SegParams& p, cudaStream_t stream);
 

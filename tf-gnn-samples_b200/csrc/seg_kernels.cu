@@ -289,6 +289,73 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_heavy_kernel(
   }
 }
 
+// Multi-CTA split of heavy targets (forward plans): a hub with thousands of incoming edges is bound by what ONE SM can
+// ingest (7,278 edges x 1 KB = 7.4 MB through one CTA = 150 us on the Zipf-skewed PPI batch).  Every RGNN_HEAVY_CHUNK edges
+// of a heavy segment are one work item: a CTA reduces it to a partial row in scratch (8 warps, fixed combination order),
+// then one warp per heavy target adds its partial rows in item order and applies the row epilogue.  Still deterministic.
+template <int NV, int MODE, bool MAXAGG, bool SCALED, bool ACTMSG>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_heavy_part_kernel(const __grid_constant__ SegParams p) {
+  __shared__ float4 part[WARPS_PER_BLOCK][NV][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col0 = blockIdx.y * (128 * NV) + lane * 4;
+  const int nitems = min(*p.heavy_item_count, p.heavy_items_cap);
+  bool ok[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) ok[k] = (col0 + k * 128) < p.D;
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int2 vc = __ldg(reinterpret_cast<const int2*>(p.heavy_items) + it);
+    const int v = vc.x;
+    const int seg_end = __ldg(p.seg_off + v + 1);
+    const int beg = __ldg(p.seg_off + v) + vc.y * p.heavy_chunk;
+    const int end = min(seg_end, beg + p.heavy_chunk);
+    float4 acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = f4(MAXAGG ? -FLT_MAX : 0.0f);
+    seg_accumulate<NV, MODE, MAXAGG, SCALED, ACTMSG>(p, v, col0, lane, ok, beg, end, warp, WARPS_PER_BLOCK, acc);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) part[warp][k][lane] = acc[k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float4 t = part[0][k][lane];
+#pragma unroll
+        for (int w = 1; w < WARPS_PER_BLOCK; ++w) t = MAXAGG ? max4(t, part[w][k][lane]) : add4(t, part[w][k][lane]);
+        if (ok[k]) *reinterpret_cast<float4*>(p.heavy_scratch + (size_t)it * p.D + col0 + k * 128) = t;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int NV, bool MAXAGG>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_heavy_finish_kernel(const __grid_constant__ SegParams p) {
+  const int lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * (128 * NV) + lane * 4;
+  const int nheavy = *p.heavy_count;
+  bool ok[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) ok[k] = (col0 + k * 128) < p.D;
+  for (int i = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); i < nheavy; i += gridDim.x * WARPS_PER_BLOCK) {
+    const int v = __ldg(p.heavy_list + i);
+    const int deg = __ldg(p.seg_off + v + 1) - __ldg(p.seg_off + v);
+    const int base = __ldg(p.heavy_base + i), n = (deg + p.heavy_chunk - 1) / p.heavy_chunk;
+    float4 acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = f4(MAXAGG ? -FLT_MAX : 0.0f);
+    for (int c = 0; c < n; ++c) {                       // fixed order: deterministic
+      const float* row = p.heavy_scratch + (size_t)(base + c) * p.D + col0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        if (ok[k]) {
+          const float4 t = *reinterpret_cast<const float4*>(row + k * 128);
+          acc[k] = MAXAGG ? max4(acc[k], t) : add4(acc[k], t);
+        }
+    }
+    seg_finish<NV>(p, v, col0, lane, ok, deg, acc);
+  }
+}
+
 // ---- RGDCN (gnns/rgdcn.py:121-171): per-channel K x K kernels that depend on the TARGET ----------------------
 // One warp per target; lane owns NV float4 of the D = C*K state (column 4*lane + 128*k), i.e. 4 outputs j0..j0+3 of
 // one channel c.  The K/4 lanes of a channel are consecutive (K is a power of two <= 128), so the K inputs of the
@@ -654,6 +721,14 @@ static void launch_seg_pair(const SegParams& p, dim3 grid, cudaStream_t stream) 
   launch_pdl(seg_reduce_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
   count_launch();
   if (p.heavy_threshold > 0 && p.heavy_known != 0) {   // unknown (-1) or > 0: a few persistent CTAs walk the heavy list
+    if (p.heavy_scratch != nullptr && p.heavy_items != nullptr) {   // multi-CTA split: partial rows per work item, then one warp per target
+      const unsigned ix = p.heavy_items_known > 0 ? (unsigned)(p.heavy_items_known < 1184 ? p.heavy_items_known : 1184) : 296u;
+      seg_reduce_heavy_part_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG><<<dim3(ix, grid.y), WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+      const unsigned fx = p.heavy_known > 0 ? (unsigned)((p.heavy_known + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK) : 148u;
+      seg_reduce_heavy_finish_kernel<NV, MAXAGG><<<dim3(fx, grid.y), WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+      count_launch(2);
+      return;
+    }
     const unsigned gx = p.heavy_known > 0 ? (unsigned)(p.heavy_known < 592 ? p.heavy_known : 592) : 148u;
     seg_reduce_heavy_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG><<<dim3(gx, grid.y), WARPS_PER_BLOCK * 32, 0, stream>>>(p);
     count_launch();
@@ -717,7 +792,15 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
       if (p.num_incoming != nullptr) launch_pdl(seg_reduce_half_kernel<true>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
       else launch_pdl(seg_reduce_half_kernel<false>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
       count_launch();
-      if (p.heavy_threshold > 0 && p.heavy_known != 0) {   // heavy targets: same split kernel as the standard path
+      if (p.heavy_threshold > 0 && p.heavy_known != 0 && p.heavy_scratch != nullptr && p.heavy_items != nullptr) {
+        const dim3 g128(1, (p.D + 127) / 128);
+        const unsigned ix = p.heavy_items_known > 0 ? (unsigned)(p.heavy_items_known < 1184 ? p.heavy_items_known : 1184) : 296u;
+        const unsigned fx = p.heavy_known > 0 ? (unsigned)((p.heavy_known + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK) : 148u;
+        if (p.num_incoming != nullptr) seg_reduce_heavy_part_kernel<1, MSG_LINEAR, false, true, false><<<dim3(ix, g128.y), WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+        else seg_reduce_heavy_part_kernel<1, MSG_LINEAR, false, false, false><<<dim3(ix, g128.y), WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+        seg_reduce_heavy_finish_kernel<1, false><<<dim3(fx, g128.y), WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+        count_launch(2);
+      } else if (p.heavy_threshold > 0 && p.heavy_known != 0) {   // heavy targets without scratch: one CTA per target
         const unsigned hx = p.heavy_known > 0 ? (unsigned)(p.heavy_known < 592 ? p.heavy_known : 592) : 148u;
         const dim3 hgrid(hx, (p.D + 127) / 128);
         if (p.num_incoming != nullptr) seg_reduce_heavy_kernel<1, MSG_LINEAR, false, true, false><<<hgrid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
