@@ -294,7 +294,11 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
     // prefetch has to live in the other group's time slot, not inside this thread's store phase.
     const int group = (warp - PROD_WARP0) / TC_GROUP_WARPS;
     const int ptid = tid - 32 * PROD_WARP0 - group * TC_GROUP_THREADS;
-    const int total_q = my_tiles * nchunks;
+    // Groups in use: never more than ring stages.  A group that has published chunk q waits for the stage of chunk q + G; with
+    // G > S that stage's "empty" barrier can still be TWO phases behind the awaited one, and an mbarrier parity wait cannot
+    // tell "two behind" from "done" (the producer would overwrite a stage the tensor core has not read yet).
+    const int ngroups = S < TC_GROUPS ? S : TC_GROUPS;
+    const int total_q = group < ngroups ? my_tiles * nchunks : 0;
     auto load_a_chunk = [&](int q, float4 (&v)[8]) {
       const int ti_idx = q / nchunks, c = q - ti_idx * nchunks;
       const TileInfo ti = decode_tile<CL>(p, cid + ti_idx * ncl, cr);
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
     };
     float4 va[8];
     if (group < total_q) load_a_chunk(group, va);
-    for (int q = group; q < total_q; q += TC_GROUPS) {
+    for (int q = group; q < total_q; q += ngroups) {
       const int s = q % S;
       const int use = q / S;
       if (use > 0) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
       fence_proxy_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(full0 + 8 * s);
       if (ptid == 0 && q < 16) TC_TRACE(2 + q);
-      if (q + TC_GROUPS < total_q) load_a_chunk(q + TC_GROUPS, va);
+      if (q + ngroups < total_q) load_a_chunk(q + ngroups, va);
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (one thread) ===========================

@@ -136,10 +136,13 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// peer rows change between exchanges and L1 is not coherent with remote writes: read them with system-scope (volatile) loads
+// Peer rows change between exchanges and L1 is not coherent with remote writes: read them with .cg loads (no L1 allocation;
+// the lines come from the owner's L2 over NVLink).  NOT ld.volatile: volatile accesses are not coalesced, and 16-byte
+// requests over NVLink gave 300 GB/s per rank on 8 GPUs (gpurun_out/r02_bench_d_n8.json) where 128-byte requests do better.
+// Ordering: the rows are only read after this CTA's acquire of the owners' flags + __syncthreads().
 __device__ __forceinline__ float4 ld_peer4(const float* p) {
   float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -149,11 +152,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 constexpr int HALO_THREADS = 512;
-constexpr int HALO_ROWS_IN_FLIGHT = 4;
+constexpr int HALO_ROWS_IN_FLIGHT = 8;
 
 // Every CTA: (1) learn the epoch e of this exchange; (2) CTA 0 tells every peer "my owned rows of this buffer are final"
 // (release: the layer kernel that wrote them ran earlier on this stream); (3) wait until every peer has said the same
-// (acquire); (4) pull: one warp per halo row, 4 rows in flight per warp, 16 bytes per lane per load.  The last CTA to finish
+// (acquire); (4) pull: one warp per halo row, 8 rows in flight per warp, 16 bytes per lane per load.  The last CTA to finish
 // publishes the new epoch.  Safe reuse of the two state buffers: a rank overwrites buffer b again only after passing the
 // barrier of a LATER exchange, which every peer enters only after its pull from b has completed.
 __global__ void __launch_bounds__(HALO_THREADS) halo_pull_kernel(const __grid_constant__ HaloPullParams p) {

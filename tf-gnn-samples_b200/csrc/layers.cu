@@ -546,8 +546,11 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
   Arena ar(workspace, workspace_bytes);
   float* T = ar.floats((size_t)V * L * D);
   float* m = ar.floats((size_t)V * D);
-  float* z = ar.floats((size_t)V * D);
-  float* rh = ar.floats((size_t)V * D);
+  static const int slab_env = getenv("RGNN_GRU_SLAB") ? atoi(getenv("RGNN_GRU_SLAB")) : 0;   // rows per slab (experiment knob)
+  const int slab_default = 2 * 148 * 128;                                     // two waves of 128-row tiles
+  const int slab = slab_env > 0 ? slab_env : (V < slab_default ? (V > 0 ? V : 1) : slab_default);
+  float* z = ar.floats((size_t)slab * D);
+  float* rh = ar.floats((size_t)slab * D);
   float* buf[2] = {ar.floats((size_t)V * D), ar.floats((size_t)V * D)};
   SegParams heavy;
   seg_heavy_scratch(heavy, plan, ar, D);
@@ -571,18 +574,30 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
       g.N = D; g.C = dst; g.ldc = D; g.epi = EPI_STORE; g.act = activation;
       RGNN_PROPAGATE(run_gemm(g, ar, stream));
     } else {                                                                  // GRUCell, gates z|r|h (A.4)
-      g.A2 = cur; g.lda2 = D; g.K2 = D;
-      g.B1 = cell_kernel; g.ldb1 = 3 * D; g.B2 = cell_recurrent_kernel; g.ldb2 = 3 * D;
-      g.N = 2 * D; g.C = z; g.ldc = D; g.C2 = rh; g.ldc2 = D; g.aux_h = cur; g.ld_h = D;
-      g.epi = EPI_GRU_ZR;
-      RGNN_PROPAGATE(run_gemm(g, ar, stream));
-      GemmParams o;
-      o.A1 = m; o.lda1 = D; o.K1 = D; o.A2 = rh; o.lda2 = D; o.K2 = D;
-      o.B1 = cell_kernel + 2 * D; o.ldb1 = 3 * D; o.B2 = cell_recurrent_kernel + 2 * D; o.ldb2 = 3 * D;
-      o.M = plan->Vt; o.N = D; o.bias = cell_bias + 2 * D; o.C = dst; o.ldc = D;
-      o.aux_h = cur; o.ld_h = D; o.aux_z = z; o.ld_z = D;
-      o.epi = EPI_GRU_OUT; o.act = activation;
-      RGNN_PROPAGATE(run_gemm(o, ar, stream));
+      // Two GEMMs per row SLAB: [z | r.h] = hs([m|h].[W_zr;U_zr] + b), then h' = z.h + (1-z).act([m | r.h].[W_h;U_h] + b_h).
+      // z and r.h live in slab-sized scratch that every slab overwrites: with ~38k rows per slab (two waves of 128-row
+      // tiles on 148 SMs) the slab's z, r.h, m and h rows (4 x 19 MB) stay in the 126 MB L2 between the two kernels and the
+      // dirty z / r.h lines are overwritten before they are evicted -- the round trip through HBM of round 1
+      // (4 x 92 MB per timestep on the QM9-10k batch) becomes L2 traffic.
+      const int Vc = plan->Vt;
+      for (int r0 = 0; r0 < Vc; r0 += slab) {
+        const int rows = (Vc - r0 < slab) ? Vc - r0 : slab;
+        const size_t off = (size_t)r0 * D;
+        GemmParams g2 = g;
+        g2.A1 = m + off; g2.M = rows;
+        g2.A2 = cur + off; g2.lda2 = D; g2.K2 = D;
+        g2.B1 = cell_kernel; g2.ldb1 = 3 * D; g2.B2 = cell_recurrent_kernel; g2.ldb2 = 3 * D;
+        g2.N = 2 * D; g2.C = z; g2.ldc = D; g2.C2 = rh; g2.ldc2 = D; g2.aux_h = cur + off; g2.ld_h = D;
+        g2.epi = EPI_GRU_ZR;
+        RGNN_PROPAGATE(run_gemm(g2, ar, stream));
+        GemmParams o;
+        o.A1 = m + off; o.lda1 = D; o.K1 = D; o.A2 = rh; o.lda2 = D; o.K2 = D;
+        o.B1 = cell_kernel + 2 * D; o.ldb1 = 3 * D; o.B2 = cell_recurrent_kernel + 2 * D; o.ldb2 = 3 * D;
+        o.M = rows; o.N = D; o.bias = cell_bias + 2 * D; o.C = dst + off; o.ldc = D;
+        o.aux_h = cur + off; o.ld_h = D; o.aux_z = z; o.ld_z = D;
+        o.epi = EPI_GRU_OUT; o.act = activation;
+        RGNN_PROPAGATE(run_gemm(o, ar, stream));
+      }
     }
     cur = dst;
   }
