@@ -31,7 +31,7 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                    // fp32 elements per 128-byte swizzle row
 #ifndef RGNN_TC_GROUPS
-#define RGNN_TC_GROUPS 2
+#define RGNN_TC_GROUPS 3
 #endif
 constexpr int TC_GROUPS = RGNN_TC_GROUPS;    // producer groups take K chunks round-robin (see the producer loop): bytes of A in flight per CTA = TC_GROUPS x 16 KB
 constexpr int TC_GROUP_WARPS = 4;            // one group covers the 128-row tile: 4 warps x 32 rows of TMEM lanes
@@ -420,10 +420,14 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
     const bool is_prod = warp >= PROD_WARP0;
     const int quarter = warp & 3;
     const int pgroup = is_prod ? (warp - PROD_WARP0) / TC_GROUP_WARPS : 0;
+    // Only the producer groups that produced (pgroup < ngroups_wb) help: they reach this point after publishing the last
+    // tile's chunks, i.e. at most one tfull phase early.  An idle group would arrive many phases early, and a parity wait
+    // cannot tell those apart (it would read the accumulator of an earlier tile).
+    const int ngroups_wb = S < TC_GROUPS ? S : TC_GROUPS;
     const uint32_t stage_q = is_prod ? ring + (uint32_t)((pgroup * 4 + quarter) * 32) * EPI_PITCH
                                      : estage + (uint32_t)(quarter * 32) * EPI_PITCH;
     const int cb_last = is_prod ? (1 + pgroup) * EPI_COLS : 0;
-    for (int it = is_prod ? my_tiles - 1 : 0; it < my_tiles; ++it) {
+    for (int it = is_prod ? (pgroup < ngroups_wb ? my_tiles - 1 : my_tiles) : 0; it < my_tiles; ++it) {
       const int a = it & 1;
       const TileInfo ti = decode_tile<CL>(p, cid + it * ncl, cr);
       mbar_wait(tfull0 + 8 * a, (it >> 1) & 1);
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
       const bool last = (it == my_tiles - 1);
       if (lane == 0 && warp == 0 && it == 0) TC_TRACE(50);
       if (lane == 0 && warp == PROD_WARP0) TC_TRACE(52);
-      epilogue_blocks<EPI>(p, ti, lane_base, stage_q, quarter, lane, last ? cb_last : 0, last ? (TC_GROUPS + 1) * EPI_COLS : EPI_COLS);
+      epilogue_blocks<EPI>(p, ti, lane_base, stage_q, quarter, lane, last ? cb_last : 0, last ? (ngroups_wb + 1) * EPI_COLS : EPI_COLS);
       if (lane == 0 && warp == 0 && it == 0) TC_TRACE(51);
       if (lane == 0 && warp == PROD_WARP0) TC_TRACE(53);
       tc_fence_before_sync();

@@ -624,8 +624,11 @@ extern "C" int rgnn_rgat_forward(const rgnn_plan_t* plan, const float* h, int32_
   }
   Arena ar(workspace, workspace_bytes);
   float* T = ar.floats((size_t)V * L * D);
-  float* ssrc = ar.floats((size_t)V * L * K);
-  float* stgt = ar.floats((size_t)V * L * K);
+  // per-edge logits: computed inside the edge kernel when a head's dh/4 lanes form a power-of-two group inside one warp
+  const int dh = D / K, lph = dh / 4;
+  const bool fused_scores = (dh % 4) == 0 && lph >= 1 && lph <= 32 && (lph & (lph - 1)) == 0 && getenv("RGNN_RGAT_UNFUSED") == nullptr;
+  float* ssrc = fused_scores ? nullptr : ar.floats((size_t)V * L * K);
+  float* stgt = fused_scores ? nullptr : ar.floats((size_t)V * L * K);
   float* buf[2] = {nullptr, nullptr};
   if (num_timesteps > 1) { buf[0] = ar.floats((size_t)V * D); buf[1] = ar.floats((size_t)V * D); }
   RGNN_PROPAGATE(check_ws(ar, "rgat"));
@@ -635,9 +638,9 @@ extern "C" int rgnn_rgat_forward(const rgnn_plan_t* plan, const float* h, int32_
   for (int t = 0; t < num_timesteps; ++t) {                                   // rgat.py:83
     float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
     RGNN_PROPAGATE(gemm_shared_a(ar, cur, V, din, edge_weights, L, D, D, T, RGNN_ACT_LINEAR, stream));   // rgat.py:95-96
-    RGNN_PROPAGATE(launch_rgat_scores(T, V, L, D, K, at, ssrc, stgt, stream));                      // rgat.py:106-115 (per node)
+    if (!fused_scores) RGNN_PROPAGATE(launch_rgat_scores(T, V, L, D, K, at, ssrc, stgt, stream));   // rgat.py:106-115 (per node)
     RgatParams r;
-    r.V = V; r.L = L; r.D = D; r.K = K;
+    r.V = V; r.L = L; r.D = D; r.K = K; r.att = at;
     r.seg_off = plan->seg_off; r.e_src = plan->e_src; r.e_type = plan->e_type;
     r.table = T; r.s_src = ssrc; r.s_tgt = stgt; r.act_out = activation; r.out = dst;
     RGNN_PROPAGATE(launch_seg_rgat(r, stream));                                                      // rgat.py:120-138

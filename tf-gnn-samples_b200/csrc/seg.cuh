@@ -47,8 +47,10 @@ struct SegParams {
 };
 int launch_seg_reduce(const SegParams& p, cudaStream_t stream);
 
+struct AttnTable { const float* att[RGNN_MAX_EDGE_TYPES]; };
 struct RgatParams {
   int V = 0, L = 1, D = 0, K = 1;
+  AttnTable att;                       // per-type attention vectors [2D] (fused-score path: s_src / s_tgt are NULL)
   const int32_t* seg_off = nullptr;
   const int32_t* e_src = nullptr;
   const int32_t* e_type = nullptr;
@@ -76,7 +78,6 @@ struct RgdcnParams {
 };
 int launch_rgdcn_edges(const RgdcnParams& p, cudaStream_t stream);
 
-struct AttnTable { const float* att[RGNN_MAX_EDGE_TYPES]; };
 // s_src[n,l,k] = <att_l[k*2d : k*2d+d], T[n,l,k*d:(k+1)*d]>, s_tgt with att_l[k*2d+d : (k+1)*2d]  (rgat.py:106-115)
 int launch_rgat_scores(const float* table, int V, int L, int D, int K, const AttnTable& att, float* s_src,
                        float* s_tgt, cudaStream_t stream);

@@ -445,29 +445,39 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) rgdcn_edge_kernel(const 
 }
 
 // ---- RGAT: per-target, per-head online softmax fused with the weighted sum -----------------
-template <int NV>
+// FUSED: the per-edge logit  a_src . T[u,l,k] + a_tgt . T[v,l,k]  (rgat.py:106-115) is computed HERE from the source row the
+// warp has just gathered (4 FMAs + a butterfly over the dh/4 lanes of the head) and from the target's own row, read once per
+// (target, type) run -- the separate per-node score kernel and its [V, L, K] tables are gone.  Needs dh/4 to be a power of
+// two <= 32 (heads must not straddle warps); otherwise the scores come from rgat_scores_kernel as before.
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w); }
+
+template <int NV, bool FUSED>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __grid_constant__ RgatParams p) {
   const int lane = threadIdx.x & 31;
   const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (v >= p.V) return;
   const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  pdl_wait();                          // T comes from the transform GEMM launched just before
+  pdl_launch_dependents();
   const int dh = p.D / p.K;   // per-head width, multiple of 4 (checked on the host)
+  const int lph = dh >> 2;    // lanes per head
   const int col0 = blockIdx.y * (128 * NV) + lane * 4;   // heads are independent: a warp owns a column slice
 
   bool ok[NV];
   int head[NV];
-  float4 acc[NV];
-  float mx[NV], den[NV];
+  float4 acc[NV], a_src[NV], a_tgt[NV];
+  float mx[NV], den[NV], s_t[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int col = col0 + k * 128;
     ok[k] = col < p.D;
     head[k] = ok[k] ? col / dh : 0;
-    acc[k] = f4(0.0f);
+    acc[k] = f4(0.0f); a_src[k] = f4(0.0f); a_tgt[k] = f4(0.0f);
     mx[k] = -INFINITY;
-    den[k] = 0.0f;
+    den[k] = 0.0f; s_t[k] = 0.0f;
   }
   const size_t LK = (size_t)p.L * p.K;
+  int cur_type = -1;
 
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int n = min(32, end - e0);
@@ -485,19 +495,42 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __
           const int src = __shfl_sync(0xffffffffu, my_src, j + u);
           const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
           const float* row = p.table + ((size_t)src * p.L + ty) * p.D + col0;
-          const float* ss = p.s_src + (size_t)src * LK + (size_t)ty * p.K;
-          const float* st = p.s_tgt + (size_t)v * LK + (size_t)ty * p.K;
 #pragma unroll
-          for (int k = 0; k < NV; ++k)
-            if (ok[k]) {
-              r[u][k] = ldg4(row + k * 128);
-              lg[u][k] = __ldg(ss + head[k]) + __ldg(st + head[k]);
-            }
+          for (int k = 0; k < NV; ++k) {
+            r[u][k] = ok[k] ? ldg4(row + k * 128) : f4(0.0f);
+            if (!FUSED && ok[k])
+              lg[u][k] = __ldg(p.s_src + (size_t)src * LK + (size_t)ty * p.K + head[k]) + __ldg(p.s_tgt + (size_t)v * LK + (size_t)ty * p.K + head[k]);
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if (j + u < n) {
+          if (FUSED) {
+            const int ty = __shfl_sync(0xffffffffu, my_type, j + u);
+            if (ty != cur_type) {        // warp-uniform: new (target, type) run -> this type's attention vector, the target's score
+              cur_type = ty;
+              const float* trow = p.table + ((size_t)v * p.L + ty) * p.D + col0;
+#pragma unroll
+              for (int k = 0; k < NV; ++k) {
+                float part = 0.0f;
+                if (ok[k]) {
+                  const float* a = p.att.att[ty] + (size_t)head[k] * 2 * dh + ((col0 + k * 128) - head[k] * dh);   // rgat.py:110-111
+                  a_src[k] = ldg4(a);
+                  a_tgt[k] = ldg4(a + dh);
+                  part = dot4(ldg4(trow + k * 128), a_tgt[k]);
+                }
+                for (int o = lph >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                s_t[k] = part;
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              float part = ok[k] ? dot4(r[u][k], a_src[k]) : 0.0f;
+              for (int o = lph >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+              lg[u][k] = part + s_t[k];
+            }
+          }
 #pragma unroll
           for (int k = 0; k < NV; ++k)
             if (ok[k]) {
@@ -823,7 +856,8 @@ int launch_seg_rgat(const RgatParams& p, cudaStream_t stream) {
   if (p.V == 0) return RGNN_OK;
   // one warp per 128-column slice of a target row (heads are independent; more resident warps win here)
   const dim3 grid((p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (p.D + 127) / 128);
-  seg_rgat_kernel<1><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+  if (p.s_src == nullptr) RGNN_CHECK_CUDA(launch_pdl(seg_rgat_kernel<1, true>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p));
+  else RGNN_CHECK_CUDA(launch_pdl(seg_rgat_kernel<1, false>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p));
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return RGNN_OK;
