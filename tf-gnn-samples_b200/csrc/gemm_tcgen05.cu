@@ -30,6 +30,9 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                    // fp32 elements per 128-byte swizzle row
+#ifndef RGNN_PAIR_DEFAULT
+#define RGNN_PAIR_DEFAULT 0                  // 1: large-M, wide-tile contractions use CTA pairs unless RGNN_GEMM_PAIR=0
+#endif
 #ifndef RGNN_TC_GROUPS
 #define RGNN_TC_GROUPS 3
 #endif
@@ -236,13 +239,22 @@ __device__ __forceinline__ void epilogue_blocks(const TcParams& p, const TileInf
 // GATHER: A rows follow an index list (GemmParams::a_rows: the compact (source, type) transform).  A separate instance,
 // so that the common kernel stays under the ~2048-instruction L1.5 I-cache (the 16 extra index loads + selects of the
 // gathered form pushed every variant over it: 86.9 -> 107 us on the headline step, gpurun_out r02 job B).
-template <int EPI, int CL, bool GATHER = false>
+// PAIR (CL == 2): tcgen05 cta_group::2.  The two CTAs of a cluster work on two consecutive m-tiles of one n-tile as ONE
+// 256 x BN MMA issued by the leader (cluster rank 0): each CTA produces the A images of its own 128 rows and streams only
+// HALF of every weight-image chunk (rows [rank * BN/2, +BN/2) of the hi and of the lo image) into its own shared memory --
+// the tensor cores read both halves.  Per CTA and chunk that is 16 KB of A + BN * 128 B of B instead of 16 KB + BN * 256 B:
+// the per-SM operand ingest, which bounds this kernel on large M, nearly halves, and the stage shrinks so
+// that a third ring stage fits at BN = 256.  Protocol: every CTA keeps its own full / empty barriers; the peer's MMA warp
+// forwards "my stage is full" to the leader's barrier (remote arrive); the leader's commits are multicast to both CTAs'
+// empty / accumulator-full barriers; the peer's epilogue warps release the accumulator on the leader's barrier.
+template <int EPI, int CL, bool GATHER = false, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const GemmParams& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN, S = p.stages;
-  const int b_img_bytes = BN * 128;
+  const int b_img_bytes = PAIR ? (BN / 2) * 128 : BN * 128;   // PAIR: this CTA holds half of the chunk's weight rows
   const int stage_bytes = 2 * A_IMG_BYTES + 2 * b_img_bytes;
   const int nchunks = p.chunks1 + p.chunks2;
   // shared-memory map (32-bit shared addresses): operand ring | epilogue staging | barriers | tmem slot
@@ -260,19 +272,25 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   if (tid == 0) TC_TRACE(0);
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full0 + 8 * s, TC_GROUP_THREADS + 1);   // one producer group + the B loader's expect_tx arrival
-      mbar_init(empty0 + 8 * s, CL);                    // one tcgen05.commit from every CTA of the cluster
+      // one producer group + the B loader's expect_tx arrival (+ the peer's "my stage is full" on the leader of a pair)
+      mbar_init(full0 + 8 * s, TC_GROUP_THREADS + 1 + ((PAIR && cr == 0) ? 1 : 0));
+      mbar_init(empty0 + 8 * s, PAIR ? 1 : CL);         // one tcgen05.commit from every issuing CTA (a pair: the leader only)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);                     // accumulator complete (tcgen05.commit)
-      mbar_init(tempty0 + 8 * a, EPI_WARPS);            // accumulator drained (one lane per epilogue warp)
+      mbar_init(tempty0 + 8 * a, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // accumulator drained (one lane per epilogue warp, both CTAs of a pair)
     }
     fence_barrier_init();
   }
   __syncwarp();
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -348,17 +366,32 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (one thread) ===========================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+    if (PAIR && cr != 0) {
+      // peer of a pair: no MMAs to issue -- forward "this CTA's stage is full" (A images written and fenced by the producers,
+      // weight half landed) to the leader's barrier, chunk by chunk
+      if (lane == 0) {
+        const int total_q = my_tiles * nchunks;
+        for (int q = 0; q < total_q; ++q) {
+          const int s = q % S;
+          mbar_wait(full0 + 8 * s, (q / S) & 1);
+          mbar_arrive_remote(full0 + 8 * s, 0);
+        }
+      }
+    } else if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(PAIR ? 2 * TC_BM : TC_BM, BN);
       int q = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int a = it & 1;
-        if (it >= 2) mbar_wait(tempty0 + 8 * a, ((it >> 1) - 1) & 1);   // epilogue has drained this accumulator
+        if (it >= 2) {                                                  // the epilogue(s) have drained this accumulator
+          if (PAIR) mbar_wait_cluster(tempty0 + 8 * a, ((it >> 1) - 1) & 1);
+          else mbar_wait(tempty0 + 8 * a, ((it >> 1) - 1) & 1);
+        }
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * acc_cols);
         for (int c = 0; c < nchunks; ++c, ++q) {
           const int s = q % S;
-          mbar_wait(full0 + 8 * s, (q / S) & 1);
+          if (PAIR) mbar_wait_cluster(full0 + 8 * s, (q / S) & 1);
+          else mbar_wait(full0 + 8 * s, (q / S) & 1);
           tc_fence_after_sync();
           if (q < 16) TC_TRACE(18 + q);
           const uint32_t a_hi = ring + (uint32_t)(s * stage_bytes);
@@ -370,15 +403,23 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (>>4 units)
             const uint64_t adv = (uint64_t)(k * 2);
-            umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, (c | k) != 0);   // small terms first
-            umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
-            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1);
+            if (PAIR) {
+              umma_tf32_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, (c | k) != 0);
+              umma_tf32_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
+              umma_tf32_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, 1);
+            } else {
+              umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, (c | k) != 0);   // small terms first
+              umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
+              umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1);
+            }
           }
-          if (CL > 1) umma_commit_multicast(empty0 + 8 * s, cl_mask);   // every CTA's loaders learn that this CTA is done with stage s
+          if (PAIR) umma_commit_pair(empty0 + 8 * s, cl_mask);          // both CTAs' loaders: stage s is reusable
+          else if (CL > 1) umma_commit_multicast(empty0 + 8 * s, cl_mask);   // every CTA's loaders learn that this CTA is done with stage s
           else umma_commit(empty0 + 8 * s);         // stage reusable once these MMAs have read it
           if (q < 16) TC_TRACE(34 + q);
         }
-        umma_commit(tfull0 + 8 * a);                // accumulator complete -> epilogue
+        if (PAIR) umma_commit_pair(tfull0 + 8 * a, cl_mask);            // accumulator complete -> both CTAs' epilogues
+        else umma_commit(tfull0 + 8 * a);           // accumulator complete -> epilogue
       }
     }
     __syncwarp();
@@ -394,10 +435,14 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
           const int use = q / S;
           if (use > 0) mbar_wait(empty0 + 8 * s, (use - 1) & 1);
           const uint32_t b_hi = ring + (uint32_t)(s * stage_bytes + 2 * A_IMG_BYTES);
-          mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);   // the whole chunk lands here, 1/CL from each CTA
+          mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_img_bytes);   // the whole chunk lands here, 1/CL from each CTA (a pair: this CTA's half)
           if (q == 0) TC_TRACE(55);
           TC_TRACE(56);
-          if (CL > 1) {
+          if (PAIR) {   // rows [cr * BN/2, +BN/2) of the hi image and of the lo image, packed back to back in this CTA's stage
+            const char* chunk = reinterpret_cast<const char*>(src_tile + (size_t)c * 2 * (BN * TC_BK));
+            bulk_copy_g2s(b_hi, chunk + (size_t)cr * b_img_bytes, b_img_bytes, full0 + 8 * s);
+            bulk_copy_g2s(b_hi + b_img_bytes, chunk + (size_t)BN * 128 + (size_t)cr * b_img_bytes, b_img_bytes, full0 + 8 * s);
+          } else if (CL > 1) {
             const uint32_t part = (uint32_t)(2 * b_img_bytes) / CL;
             bulk_copy_g2s_multicast(b_hi + cr * part, reinterpret_cast<const char*>(src_tile + (size_t)c * 2 * (BN * TC_BK)) + (size_t)cr * part,
                                     part, full0 + 8 * s, cl_mask);
@@ -442,7 +487,10 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
       if (lane == 0 && warp == PROD_WARP0) TC_TRACE(53);
       tc_fence_before_sync();
       __syncwarp();
-      if (!is_prod && lane == 0) mbar_arrive(tempty0 + 8 * a);  // this warp's TMEM lanes of accumulator a are drained
+      if (!is_prod && lane == 0) {                               // this warp's TMEM lanes of accumulator a are drained
+        if (PAIR && cr != 0) mbar_arrive_remote(tempty0 + 8 * a, 0);   // the leader issues the MMAs that overwrite it
+        else mbar_arrive(tempty0 + 8 * a);
+      }
     }
   }
 
@@ -453,7 +501,8 @@ __global__ void __launch_bounds__(TC_THREADS_V4, 1) gemm_tcgen05_kernel(const __
   if (CL > 1) cluster_sync_all();                       // no CTA leaves while peers may still multicast into it / arrive on it
   if (warp == MMA_WARP) {
     tc_fence_after_sync();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
   }
 }
 
@@ -552,6 +601,15 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   (void)m_tiles_all;
   int CL = 1;
   if (cl_env == 1 || cl_env == 2 || cl_env == 4) CL = cl_env;
+  // CTA pairs (tcgen05 cta_group::2): RGNN_GEMM_PAIR=1 forces them, =0 forbids them; default: large-M contractions with wide
+  // tiles, where the per-SM ingest of the weight images is the bound
+  static const int pair_env = getenv("RGNN_GEMM_PAIR") ? atoi(getenv("RGNN_GEMM_PAIR")) : -1;
+  bool pair = false;
+  if (g.a_rows == nullptr && CL == 1 && (p.BN % 32) == 0) {
+    if (pair_env == 1) pair = true;
+    else if (pair_env != 0) pair = RGNN_PAIR_DEFAULT && m_tiles_all >= 2 * 148 && p.BN >= 128;
+  }
+  if (pair) CL = 2;
   auto groups_of = [&](int nrows) { return (((nrows + TC_BM - 1) / TC_BM + CL - 1) / CL) * n_tiles; };
   // group table: batch entry z owns groups [tile_start[z], tile_start[z+1])
   p.tile_start[0] = 0;
@@ -567,7 +625,7 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   }
   if (p.total_tiles <= 0) return RGNN_OK;
 
-  const size_t stage_bytes = 2 * (size_t)A_IMG_BYTES + 2 * (size_t)p.BN * 128;
+  const size_t stage_bytes = 2 * (size_t)A_IMG_BYTES + 2 * (size_t)(pair ? p.BN / 2 : p.BN) * 128;
   p.stages = (int)(TC_RING_BUDGET / stage_bytes);
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 1) p.stages = 1;
@@ -656,12 +714,16 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
     }
   };
   KernelFn fn = pick(g.epi);
+  if (pair) {
+    fn = g.epi == EPI_STORE ? gemm_tcgen05_kernel<EPI_STORE, 2, false, true>
+       : g.epi == EPI_GRU_ZR ? gemm_tcgen05_kernel<EPI_GRU_ZR, 2, false, true> : gemm_tcgen05_kernel<EPI_GRU_OUT, 2, false, true>;
+  }
   if (g.a_rows != nullptr) {
     RGNN_REQUIRE(g.epi == EPI_STORE && CL == 1 && g.K2 == 0, "gemm: gathered A rows support the plain store epilogue, one K segment, no cluster");
     fn = gemm_tcgen05_kernel<EPI_STORE, 1, true>;
   }
-  static bool attr_done[MAX_DEV][4][5] = {};
-  const int attr_slot = g.a_rows != nullptr ? 3 : g.epi;
+  static bool attr_done[MAX_DEV][7][5] = {};
+  const int attr_slot = g.a_rows != nullptr ? 3 : (pair ? 4 + g.epi : g.epi);
   if (!attr_done[dv][attr_slot][CL]) {
     RGNN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
     attr_done[dv][attr_slot][CL] = true;
@@ -686,8 +748,8 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
   cfg.attrs = attr;
   cfg.numAttrs = na;
   if (CL > 1) {   // clusters of 4 cannot use every SM (GPC sizes): size the persistent grid by what is co-resident
-    static int cached_of[MAX_DEV][3][5] = {};
-    int (&cached)[3][5] = cached_of[dv];
+    static int cached_of[MAX_DEV][2][3][5] = {};
+    int (&cached)[3][5] = cached_of[dv][pair ? 1 : 0];
     if (cached[g.epi][CL] == 0) {
       cfg.gridDim = dim3((unsigned)(max_clusters * CL));
       int n = 0;

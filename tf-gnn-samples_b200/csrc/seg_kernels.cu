@@ -560,6 +560,93 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __
     }
 }
 
+// Small batches (one PPI-shaped graph: 2,245 targets) leave the kernel above with 4,490 warps -- latency-bound at 51 us for
+// 120k edges where the RGCN edge stage needs 17.5 us.  Same remedy as seg_reduce_half_kernel: a warp owns a 64-column slice and
+// its two half-warps gather two DIFFERENT edges per load instruction; each half runs its own online softmax (and its own
+// current-type state), the two (max, denominator, accumulator) states are merged with one xor-16 exchange at the end, in a
+// fixed order.  Fused scores only (lanes per head = dh/4 in {1, 2, 4, 8, 16}: a head lies inside one half-warp's 64 columns).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_half_kernel(const __grid_constant__ RgatParams p) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (v >= p.V) return;
+  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  pdl_wait();
+  pdl_launch_dependents();
+  const int dh = p.D / p.K, lph = dh >> 2;
+  const int col = blockIdx.y * 64 + l16 * 4;
+  const bool ok = col < p.D;
+  const int head = ok ? col / dh : 0;
+  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+  float4 acc = f4(0.0f), a_src = f4(0.0f), a_tgt = f4(0.0f);
+  float mx = -INFINITY, den = 0.0f, s_t = 0.0f;
+  int cur_type = -1;
+  const float* tcol = p.table + col;
+
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int n = min(32, end - e0);
+    int my_src = 0, my_type = 0;
+    if (lane < n) {
+      my_src = __ldg(p.e_src + e0 + lane);
+      my_type = __ldg(p.e_type + e0 + lane);
+    }
+    for (int j = 0; j < n; j += 2 * UNROLL) {
+      float4 r[UNROLL];
+      int ty[UNROLL];
+      bool valid[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int e = j + 2 * u + half;                 // <= 31
+        const int src = __shfl_sync(0xffffffffu, my_src, e);
+        ty[u] = __shfl_sync(0xffffffffu, my_type, e);
+        valid[u] = e < n;
+        r[u] = (valid[u] && ok) ? ldg4(tcol + ((size_t)src * p.L + ty[u]) * p.D) : f4(0.0f);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (valid[u]) {                                  // uniform inside a half-warp
+          if (ty[u] != cur_type) {                       // this half's new (target, type) run
+            cur_type = ty[u];
+            float part = 0.0f;
+            if (ok) {
+              const float* a = p.att.att[cur_type] + (size_t)head * 2 * dh + (col - head * dh);
+              a_src = ldg4(a);
+              a_tgt = ldg4(a + dh);
+              part = dot4(ldg4(tcol + ((size_t)v * p.L + cur_type) * p.D), a_tgt);
+            }
+            for (int o = lph >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(hmask, part, o);
+            s_t = part;
+          }
+          float part = ok ? dot4(r[u], a_src) : 0.0f;
+          for (int o = lph >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(hmask, part, o);
+          float x = part + s_t;
+          x = x > 0.0f ? x : 0.2f * x;                   // tf.nn.leaky_relu (rgat.py:113)
+          const float mnew = fmaxf(mx, x);
+          const float corr = expf(mx - mnew);
+          const float w = expf(x - mnew);
+          den = den * corr + w;
+          acc.x = acc.x * corr + w * r[u].x; acc.y = acc.y * corr + w * r[u].y;
+          acc.z = acc.z * corr + w * r[u].z; acc.w = acc.w * corr + w * r[u].w;
+          mx = mnew;
+        }
+      }
+    }
+  }
+  // merge the two halves' softmax states (half 0 first: fixed order)
+  const float mo = __shfl_xor_sync(0xffffffffu, mx, 16), dno = __shfl_xor_sync(0xffffffffu, den, 16);
+  const float4 ao = make_float4(__shfl_xor_sync(0xffffffffu, acc.x, 16), __shfl_xor_sync(0xffffffffu, acc.y, 16),
+                                __shfl_xor_sync(0xffffffffu, acc.z, 16), __shfl_xor_sync(0xffffffffu, acc.w, 16));
+  if (half == 0 && ok) {
+    float4 o = f4(0.0f);                                 // no incoming message -> zeros (A.7)
+    if (end > beg) {
+      const float m = fmaxf(mx, mo);                     // half 0 saw edge 0: mx is finite
+      const float c0 = expf(mx - m), c1 = expf(mo - m);  // exp(-inf) = 0 when half 1 saw no edge
+      const float d = den * c0 + dno * c1;
+      o = make_float4((acc.x * c0 + ao.x * c1) / d, (acc.y * c0 + ao.y * c1) / d, (acc.z * c0 + ao.z * c1) / d, (acc.w * c0 + ao.w * c1) / d);
+    }
+    *reinterpret_cast<float4*>(p.out + (size_t)v * p.D + col) = act4_cold(o, p.act_out);
+  }
+}
+
 // one thread per (node, type, head)
 __global__ void rgat_scores_kernel(const float* __restrict__ table, int V, int L, int D, int K,
                                    const __grid_constant__ AttnTable att, float* __restrict__ s_src,
@@ -856,7 +943,13 @@ int launch_seg_rgat(const RgatParams& p, cudaStream_t stream) {
   if (p.V == 0) return RGNN_OK;
   // one warp per 128-column slice of a target row (heads are independent; more resident warps win here)
   const dim3 grid((p.V + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (p.D + 127) / 128);
-  if (p.s_src == nullptr) RGNN_CHECK_CUDA(launch_pdl(seg_rgat_kernel<1, true>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p));
+  const int lph = (p.D / p.K) / 4;
+  static const int rgat_half_env = getenv("RGNN_RGAT_HALF") ? atoi(getenv("RGNN_RGAT_HALF")) : -1;   // 0 / 1 force, default: small batches
+  const bool half_ok = p.s_src == nullptr && lph <= 16;
+  if (half_ok && (rgat_half_env == 1 || (rgat_half_env != 0 && (long)p.V * ((p.D + 127) / 128) < 148L * 40))) {
+    const dim3 hgrid(grid.x, (p.D + 63) / 64);
+    RGNN_CHECK_CUDA(launch_pdl(seg_rgat_half_kernel, hgrid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p));
+  } else if (p.s_src == nullptr) RGNN_CHECK_CUDA(launch_pdl(seg_rgat_kernel<1, true>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p));
   else RGNN_CHECK_CUDA(launch_pdl(seg_rgat_kernel<1, false>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p));
   RGNN_CHECK_CUDA(cudaGetLastError());
   count_launch();
