@@ -127,3 +127,27 @@ def test_restricted_target_rows_sharded_execution(cuda_device):
         sparse_ggnn_layer(h, own, D, num_timesteps=2, weights=wg)
     with pytest.raises(RgnnError):
         own.set_num_targets(part.n_local + 1)
+
+
+def test_cta_pair_gemm_in_a_subprocess(cuda_device):
+    """The tcgen05 cta_group::2 variant of the GEMM (RGNN_GEMM_PAIR=1 is read once per process): dense contractions with
+    bias / activation, ragged M and N, two K segments' worth of chunks -- against float64, same 1e-5 bar as the default path."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import numpy as np, torch, sys
+        sys.path.insert(0, %r)
+        from tf_gnn_samples_b200 import ops
+        from oracle import ref_layers as R
+        rng = np.random.default_rng(0)
+        for (m, k, n) in [(1000, 128, 256), (4097, 256, 384), (300, 64, 96), (129, 32, 32)]:
+            x = rng.standard_normal((m, k)).astype(np.float32); w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+            b = rng.standard_normal(n).astype(np.float32)
+            got = ops.dense(torch.as_tensor(x).cuda(), torch.as_tensor(w).cuda(), torch.as_tensor(b).cuda(), "tanh").cpu().numpy()
+            want = np.tanh(x.astype(np.float64) @ w.astype(np.float64) + b)
+            err = R.max_norm_rel_err(got, want)
+            assert err <= 1e-5, (m, k, n, err)
+        print("PAIR_OK")
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, RGNN_GEMM_PAIR="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert "PAIR_OK" in res.stdout, res.stdout + res.stderr
