@@ -183,6 +183,7 @@ __device__ __forceinline__ void epilogue_blocks(const TcParams& p, const TileInf
   const int n0 = ti.n_tile * BN;
   for (int cb = cb_begin; cb < BN; cb += cb_step) {
     {
+#ifdef RGNN_EPI_LD16
       float v[16];
       tmem_ld16(lane_base + cb, v);
 #pragma unroll
@@ -192,6 +193,13 @@ __device__ __forceinline__ void epilogue_blocks(const TcParams& p, const TileInf
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd)
         sts128(srow_w + (uint32_t)(64 + qd * 16), make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]));
+#else
+      float v[32];                                   // the whole 32-column block of this lane's row: one TMEM round trip
+      tmem_ld32(lane_base + cb, v);
+#pragma unroll
+      for (int qd = 0; qd < 8; ++qd)
+        sts128(srow_w + (uint32_t)(qd * 16), make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]));
+#endif
     }
     __syncwarp();
     const int c = n0 + cb + sub_c4 * 4;
