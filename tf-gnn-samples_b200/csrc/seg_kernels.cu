@@ -253,6 +253,86 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_half_kernel(c
   seg_finish<1>(p, v, col0, lane, ok1, end - beg, a1);
 }
 
+// EXPERIMENT (RGNN_SEG_BULK=1; VERDICT r1 item 6: "measure a cp.async.bulk row-gather variant once"): the north star's
+// sketch -- rows pulled into shared memory by the TMA unit -- for the plain edge stage (linear messages, sum / mean / sqrt_n).
+// A warp owns a 128-column slice of one target; lane 0 issues one 512-byte cp.async.bulk per gathered row into the warp's own
+// ring (2 batches x 5 rows), completion on an mbarrier per batch; the lanes then read their float4 of every landed row from
+// shared memory and accumulate.  One bulk-copy instruction per row instead of 32 LDG.128 lanes, but every gathered byte is
+// written to and read back from shared memory once more.  Result: see DESIGN.md 5.2 / profiles/r02_seg_bulk.txt.
+constexpr int BULK_ROWS = 5;   // 8 warps x 2 batches x 5 rows x 512 B = 40 KB of static shared memory
+template <bool SCALED>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_reduce_bulk_kernel(const __grid_constant__ SegParams p) {
+  __shared__ __align__(128) float ring[WARPS_PER_BLOCK][2][BULK_ROWS][128];
+  __shared__ __align__(8) unsigned long long bars[WARPS_PER_BLOCK][2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int v = blockIdx.x * WARPS_PER_BLOCK + w;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[w][0]), bar1 = (uint32_t)__cvta_generic_to_shared(&bars[w][1]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (v >= p.V) return;
+  const int col0 = blockIdx.y * 128;                     // slice start; the slice is 128 columns (512 bytes) wide
+  const int width = min(128, p.D - col0);                // D % 4 == 0; bulk copies need multiples of 16 bytes
+  const int beg = __ldg(p.seg_off + v), end = __ldg(p.seg_off + v + 1);
+  pdl_wait();
+  pdl_launch_dependents();
+  if (p.heavy_threshold > 0 && end - beg > p.heavy_threshold) return;
+  float4 acc = f4(0.0f);
+  const bool okc = lane * 4 < width;
+  const int nb = (end - beg + BULK_ROWS - 1) / BULK_ROWS;
+  auto issue = [&](int b) {                              // batch b: edges [beg + 8b, +8) -> ring slot b & 1
+    const int e0 = beg + b * BULK_ROWS;
+    const int n = min(BULK_ROWS, end - e0);
+    float sc = 1.0f;
+    long off = 0;
+    if (lane < n) {
+      const int ty = __ldg(p.e_type + e0 + lane), idx = __ldg(p.e_idx + e0 + lane);
+      off = (long)idx * p.stride_idx + (long)ty * p.stride_type + col0;
+      if (SCALED) sc = 1.0f / (__ldg(p.num_incoming + (size_t)ty * p.scale_ld + (p.scale_by_idx ? idx : v)) + 1e-7f);
+    }
+    const uint32_t bar = (b & 1) ? bar1 : bar0;
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(n * width * 4)) : "memory");
+    __syncwarp();
+    if (lane < n) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[w][b & 1][lane][0]);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(p.table + off), "r"((uint32_t)(width * 4)), "r"(bar) : "memory");
+    }
+    return sc;
+  };
+  float sc_cur = 0.0f, sc_next = 0.0f;
+  if (nb > 0) sc_cur = issue(0);
+  for (int b = 0; b < nb; ++b) {
+    if (b + 1 < nb) sc_next = issue(b + 1);
+    const uint32_t bar = (b & 1) ? bar1 : bar0;
+    const uint32_t parity = (uint32_t)((b >> 1) & 1);
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      if (++spins > (1u << 22)) __trap();
+    }
+    const int n = min(BULK_ROWS, end - (beg + b * BULK_ROWS));
+#pragma unroll
+    for (int r = 0; r < BULK_ROWS; ++r) {
+      const float s_r = __shfl_sync(0xffffffffu, sc_cur, r);
+      if (r < n && okc) {
+        const float4 m = *reinterpret_cast<const float4*>(&ring[w][b & 1][r][lane * 4]);
+        if (SCALED) { acc.x = fmaf(m.x, s_r, acc.x); acc.y = fmaf(m.y, s_r, acc.y); acc.z = fmaf(m.z, s_r, acc.z); acc.w = fmaf(m.w, s_r, acc.w); }
+        else acc = add4(acc, m);
+      }
+    }
+    __syncwarp();                                        // every lane has read slot b & 1 before batch b + 2 overwrites it
+    sc_cur = sc_next;
+  }
+  bool ok1[1] = {okc};
+  float4 a1[1] = {acc};
+  seg_finish<1>(p, v, col0 + lane * 4, lane, ok1, end - beg, a1);
+}
+
 // Degree skew: a target with thousands of incoming edges would serialise on one warp (Zipf-skewed PPI-shaped
 // batch: 1.0 ms instead of 35 us per layer).  Here a whole CTA takes one heavy target: warp w reduces the
 // 32-edge chunks w, w+8, ..., the 8 partial rows are combined in a fixed order (still deterministic).
@@ -536,15 +616,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_kernel(const __
             if (ok[k]) {
               float x = lg[u][k];
               x = x > 0.0f ? x : 0.2f * x;                   // tf.nn.leaky_relu (rgat.py:113)
-              const float mnew = fmaxf(mx[k], x);
-              const float corr = expf(mx[k] - mnew);          // exp(-inf) = 0 on the first message
-              const float w = expf(x - mnew);
-              den[k] = den[k] * corr + w;
-              acc[k].x = acc[k].x * corr + w * r[u][k].x;
-              acc[k].y = acc[k].y * corr + w * r[u][k].y;
-              acc[k].z = acc[k].z * corr + w * r[u][k].z;
-              acc[k].w = acc[k].w * corr + w * r[u][k].w;
-              mx[k] = mnew;
+              if (x > mx[k]) {                                // new running maximum (rare after the first few messages): rescale
+                const float corr = __expf(mx[k] - x);         // exp(-inf) = 0 on the first message
+                den[k] = den[k] * corr + 1.0f;
+                acc[k].x = acc[k].x * corr + r[u][k].x; acc[k].y = acc[k].y * corr + r[u][k].y;
+                acc[k].z = acc[k].z * corr + r[u][k].z; acc[k].w = acc[k].w * corr + r[u][k].w;
+                mx[k] = x;
+              } else {                                        // one exponential per message in the common case
+                const float w = __expf(x - mx[k]);
+                den[k] += w;
+                acc[k].x = fmaf(w, r[u][k].x, acc[k].x); acc[k].y = fmaf(w, r[u][k].y, acc[k].y);
+                acc[k].z = fmaf(w, r[u][k].z, acc[k].z); acc[k].w = fmaf(w, r[u][k].w, acc[k].w);
+              }
             }
         }
       }
@@ -620,13 +703,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_half_kernel(con
           for (int o = lph >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(hmask, part, o);
           float x = part + s_t;
           x = x > 0.0f ? x : 0.2f * x;                   // tf.nn.leaky_relu (rgat.py:113)
-          const float mnew = fmaxf(mx, x);
-          const float corr = expf(mx - mnew);
-          const float w = expf(x - mnew);
-          den = den * corr + w;
-          acc.x = acc.x * corr + w * r[u].x; acc.y = acc.y * corr + w * r[u].y;
-          acc.z = acc.z * corr + w * r[u].z; acc.w = acc.w * corr + w * r[u].w;
-          mx = mnew;
+          if (x > mx) {                                  // new running maximum (rare after the first few messages): rescale
+            const float corr = __expf(mx - x);
+            den = den * corr + 1.0f;
+            acc.x = acc.x * corr + r[u].x; acc.y = acc.y * corr + r[u].y;
+            acc.z = acc.z * corr + r[u].z; acc.w = acc.w * corr + r[u].w;
+            mx = x;
+          } else {                                       // one exponential per message in the common case
+            const float w = __expf(x - mx);
+            den += w;
+            acc.x = fmaf(w, r[u].x, acc.x); acc.y = fmaf(w, r[u].y, acc.y);
+            acc.z = fmaf(w, r[u].z, acc.z); acc.w = fmaf(w, r[u].w, acc.w);
+          }
         }
       }
     }
@@ -639,7 +727,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) seg_rgat_half_kernel(con
     float4 o = f4(0.0f);                                 // no incoming message -> zeros (A.7)
     if (end > beg) {
       const float m = fmaxf(mx, mo);                     // half 0 saw edge 0: mx is finite
-      const float c0 = expf(mx - m), c1 = expf(mo - m);  // exp(-inf) = 0 when half 1 saw no edge
+      const float c0 = __expf(mx - m), c1 = __expf(mo - m);  // exp(-inf) = 0 when half 1 saw no edge
       const float d = den * c0 + dno * c1;
       o = make_float4((acc.x * c0 + ao.x * c1) / d, (acc.y * c0 + ao.y * c1) / d, (acc.z * c0 + ao.z * c1) / d, (acc.w * c0 + ao.w * c1) / d);
     }
@@ -907,7 +995,20 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
     const long warps128 = (long)p.V * ((p.D + 127) / 128);
     const bool half_ok = p.msg_mode == MSG_LINEAR && p.agg != RGNN_AGG_MAX && p.act_msg == RGNN_ACT_LINEAR && p.D >= 64;
     const bool use_half = half_ok && (half_env == 1 || (half_env != 0 && warps128 < 148L * 40));
-    if (use_half) {
+    static const bool bulk_env = getenv("RGNN_SEG_BULK") != nullptr && atoi(getenv("RGNN_SEG_BULK")) == 1;   // experiment: TMA row gather
+    if (bulk_env && half_ok && (p.stride_idx % 4) == 0) {
+      const dim3 grid(gx, (p.D + 127) / 128);
+      if (p.num_incoming != nullptr) RGNN_CHECK_CUDA(launch_pdl(seg_reduce_bulk_kernel<true>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p));
+      else RGNN_CHECK_CUDA(launch_pdl(seg_reduce_bulk_kernel<false>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p));
+      count_launch();
+      if (p.heavy_threshold > 0 && p.heavy_known != 0) {
+        const unsigned hx = p.heavy_known > 0 ? (unsigned)(p.heavy_known < 592 ? p.heavy_known : 592) : 148u;
+        const dim3 hgrid(hx, (p.D + 127) / 128);
+        if (p.num_incoming != nullptr) seg_reduce_heavy_kernel<1, MSG_LINEAR, false, true, false><<<hgrid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+        else seg_reduce_heavy_kernel<1, MSG_LINEAR, false, false, false><<<hgrid, WARPS_PER_BLOCK * 32, 0, stream>>>(p);
+        count_launch();
+      }
+    } else if (use_half) {
       const dim3 grid(gx, (p.D + 63) / 64);
       if (p.num_incoming != nullptr) launch_pdl(seg_reduce_half_kernel<true>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
       else launch_pdl(seg_reduce_half_kernel<false>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
