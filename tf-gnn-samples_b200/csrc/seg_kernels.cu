@@ -979,6 +979,18 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
       set_error("segment reduce: layer-norm epilogue supports state dim <= %d, got %d", RGNN_MAX_STATE_DIM, p.D);
       return RGNN_E_UNSUPPORTED;
     }
+    // Small batches: one warp per WHOLE row leaves too few warps to hide the gather latency (PPI-shaped Edge-MLP0: 2,245
+    // warps, 73 us).  Reduce with one warp per 128-column slice instead and normalise the finished rows in a second, tiny
+    // pass (V x D x 8 bytes; the layer-norm kernel works in place: it holds the row in registers).
+    static const int ln_split_env = getenv("RGNN_LN_SPLIT") ? atoi(getenv("RGNN_LN_SPLIT")) : -1;   // 0 / 1 force
+    const bool ln_split = p.D > 128 && p.ld_out == p.D && (ln_split_env == 1 || (ln_split_env != 0 && (long)p.V < 148L * 40));
+    if (ln_split) {
+      SegParams q = p;
+      q.ln_gamma = nullptr; q.ln_beta = nullptr;
+      launch_seg_nv<1>(q, dim3(gx, (p.D + 127) / 128), stream);
+      RGNN_CHECK_CUDA(cudaGetLastError());
+      return launch_layer_norm(p.out, p.V, p.D, p.ln_gamma, p.ln_beta, p.out, stream);
+    }
     const dim3 grid(gx, 1);
     switch (nv_for(p.D)) {
       case 1: launch_seg_nv<1>(p, grid, stream); break;
