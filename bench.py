@@ -12,7 +12,9 @@ own counter (models/sparse_graph_model.py:285,310: sum of E_l per batch, counted
   value        device-timed (CUDA events), inputs + plan resident in HBM, the 3 layers replayed as one CUDA graph,
                L2 flushed (256 MiB write) between timed steps.
   e2e          the same metric through the public Python API from pinned HOST buffers: H2D of features +
-               adjacency + in-degrees, plan build, 3 layers, D2H of the final node states -- every step.
+               adjacency + in-degrees, plan build, 3 layers, D2H of the final node states -- every step, as EAGER API
+               calls (the headline e2e); the same calls recorded once into a CUDA graph and replayed are reported
+               beside it (graph_replay_value).
   roofline     algorithmic bytes of one RGCN layer (M*(4D+12) + V*8D + L*D*D*4) / measured layer
                time, against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
   cpu_baseline the torch-CPU restatement of the reference op order (oracle/ref_torch.py) on this box's cores.

@@ -547,7 +547,7 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
   float* T = ar.floats((size_t)V * L * D);
   float* m = ar.floats((size_t)V * D);
   static const int slab_env = getenv("RGNN_GRU_SLAB") ? atoi(getenv("RGNN_GRU_SLAB")) : 0;   // rows per slab (experiment knob)
-  const int slab_default = 2 * 148 * 128;                                     // two waves of 128-row tiles
+  const int slab_default = 148 * 128;                                         // one wave of 128-row tiles (measured: 18,944 rows 1.93 ms, 37,888 2.05, 56,832 2.23 on QM9-10k)
   const int slab = slab_env > 0 ? slab_env : (V < slab_default ? (V > 0 ? V : 1) : slab_default);
   float* z = ar.floats((size_t)slab * D);
   float* rh = ar.floats((size_t)slab * D);
@@ -564,7 +564,10 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
     s.D = D;
     RGNN_PROPAGATE(transform_sources(plan, ar, cur, D, D, edge_weights, T, stream, s));   // ggnn.py:80-82
     s.agg = aggregation; s.out = m; s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;   // ggnn.py:87-90
-    RGNN_PROPAGATE(launch_seg_reduce(s, stream));
+    // GRU on a batch without heavy targets: the edge stage is slabbed together with the cell (below), so that a slab's
+    // aggregated messages are consumed out of L2 by the two cell GEMMs instead of making a round trip through HBM
+    const bool slab_edges = cell_kind == RGNN_CELL_GRU && plan->num_heavy_host == 0 && getenv("RGNN_GRU_SLAB_EDGES_OFF") == nullptr;
+    if (!slab_edges) RGNN_PROPAGATE(launch_seg_reduce(s, stream));
     GemmParams g;
     g.A1 = m; g.lda1 = D; g.K1 = D;
     g.M = plan->Vt; g.bias = cell_bias;   // the cell runs on the wanted target rows only
@@ -575,23 +578,30 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
       RGNN_PROPAGATE(run_gemm(g, ar, stream));
     } else {                                                                  // GRUCell, gates z|r|h (A.4)
       // Two GEMMs per row SLAB: [z | r.h] = hs([m|h].[W_zr;U_zr] + b), then h' = z.h + (1-z).act([m | r.h].[W_h;U_h] + b_h).
-      // z and r.h live in slab-sized scratch that every slab overwrites: with ~38k rows per slab (two waves of 128-row
-      // tiles on 148 SMs) the slab's z, r.h, m and h rows (4 x 19 MB) stay in the 126 MB L2 between the two kernels and the
+      // z and r.h live in slab-sized scratch that every slab overwrites: with ~19k rows per slab (one wave of 128-row
+      // tiles on 148 SMs) the slab's z, r.h, m, h and output rows (5 x 9.7 MB) stay in the 126 MB L2 between the two kernels and the
       // dirty z / r.h lines are overwritten before they are evicted -- the round trip through HBM of round 1
       // (4 x 92 MB per timestep on the QM9-10k batch) becomes L2 traffic.
       const int Vc = plan->Vt;
       for (int r0 = 0; r0 < Vc; r0 += slab) {
         const int rows = (Vc - r0 < slab) ? Vc - r0 : slab;
         const size_t off = (size_t)r0 * D;
+        const float* m_slab = m + off;
+        if (slab_edges) {                                  // aggregate this slab's targets into the first rows of m (reused by every slab)
+          SegParams q = s;
+          q.V = rows; q.seg_off = s.seg_off + r0; q.out = m;
+          RGNN_PROPAGATE(launch_seg_reduce(q, stream));
+          m_slab = m;
+        }
         GemmParams g2 = g;
-        g2.A1 = m + off; g2.M = rows;
+        g2.A1 = m_slab; g2.M = rows;
         g2.A2 = cur + off; g2.lda2 = D; g2.K2 = D;
         g2.B1 = cell_kernel; g2.ldb1 = 3 * D; g2.B2 = cell_recurrent_kernel; g2.ldb2 = 3 * D;
         g2.N = 2 * D; g2.C = z; g2.ldc = D; g2.C2 = rh; g2.ldc2 = D; g2.aux_h = cur + off; g2.ld_h = D;
         g2.epi = EPI_GRU_ZR;
         RGNN_PROPAGATE(run_gemm(g2, ar, stream));
         GemmParams o;
-        o.A1 = m + off; o.lda1 = D; o.K1 = D; o.A2 = rh; o.lda2 = D; o.K2 = D;
+        o.A1 = m_slab; o.lda1 = D; o.K1 = D; o.A2 = rh; o.lda2 = D; o.K2 = D;
         o.B1 = cell_kernel + 2 * D; o.ldb1 = 3 * D; o.B2 = cell_recurrent_kernel + 2 * D; o.ldb2 = 3 * D;
         o.M = rows; o.N = D; o.bias = cell_bias + 2 * D; o.C = dst + off; o.ldc = D;
         o.aux_h = cur + off; o.ld_h = D; o.aux_z = z; o.ld_z = D;
