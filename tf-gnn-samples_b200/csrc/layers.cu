@@ -693,14 +693,31 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
     seg_from_plan(s, plan);
     s.D = D;
     RGNN_PROPAGATE(transform_sources(plan, ar, cur, din, D, edge_weights, T, stream, s));                        // :94 on nodes
-    RGNN_PROPAGATE(gemm_shared_a(ar, cur, plan->Vt, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));  // :102, target rows only
     s.num_incoming = normalize ? num_incoming : nullptr;                      // :96-100
-    s.msg_mode = MSG_FILM; s.mod_table = FW; s.mod_stride_node = (long)L * 2 * D; s.mod_stride_type = 2 * D;   // :103-108
+    s.msg_mode = MSG_FILM; s.mod_stride_node = (long)L * 2 * D; s.mod_stride_type = 2 * D;                        // :103-108
     s.act_msg = activation;                                                   // :112 (before the sum)
     s.agg = aggregation;                                                      // :113-116
     s.ln_gamma = ln_gamma + (size_t)t * D; s.ln_beta = ln_beta + (size_t)t * D;   // :120
-    s.out = dst; s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;
-    RGNN_PROPAGATE(launch_seg_reduce(s, stream));
+    s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;
+    // [gamma | beta] = F_l h_v for the wanted target rows (:102), in row slabs small enough (<= 48 MB of gamma / beta rows)
+    // that the edge stage reads them back out of L2: the target-side GEMM and the edge stage alternate per slab.  Needs a
+    // plan without heavy targets (their work lists hold absolute row ids); otherwise one slab = all rows.
+    const int Vc = plan->Vt;
+    int slab = Vc > 0 ? Vc : 1;
+    if (plan->num_heavy_host == 0 && getenv("RGNN_FILM_SLAB_OFF") == nullptr) {
+      const long rows_fit = (48L << 20) / ((long)L * 2 * D * (long)sizeof(float));
+      const long r = rows_fit / 128 * 128;
+      if (r >= 1024 && r < slab) slab = (int)r;
+    }
+    for (int r0 = 0; r0 < Vc; r0 += slab) {
+      const int rows = (Vc - r0 < slab) ? Vc - r0 : slab;
+      RGNN_PROPAGATE(gemm_shared_a(ar, cur + (size_t)r0 * din, rows, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));
+      SegParams q = s;
+      q.V = rows; q.seg_off = s.seg_off + r0; q.mod_table = FW;             // FW holds this slab's rows from row 0
+      if (q.num_incoming != nullptr) q.num_incoming = s.num_incoming + r0;    // c[type, v] = base[type * ld + v]
+      q.out = dst + (size_t)r0 * D;
+      RGNN_PROPAGATE(launch_seg_reduce(q, stream));
+    }
     cur = dst; din = D;
   }
   return RGNN_OK;
