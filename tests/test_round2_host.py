@@ -54,3 +54,34 @@ def test_big_case_summary_bounds_follow_from_the_elementwise_tolerance():
     assert max(RC.compare_with_summary(biased, z)) <= eps * (1 + 1e-9)
     spoiled = out.copy(); spoiled[501, 7] += 1.0                                    # one bad element in an uncommitted row is seen
     assert max(RC.compare_with_summary(spoiled, z)) > 1e-4
+
+
+def test_tf1_optimizer_update_rules():
+    """TF 1.13 RMSProp (ms slot starts at one, epsilon inside the sqrt) and Adam (epsilon-hat form) by hand; a parameter
+    without a gradient decays like TF's zero-gradient update."""
+    import torch
+    from tf_gnn_samples_b200.tf_optimizers import TF1Adam, TF1RMSProp
+    w = torch.nn.Parameter(torch.tensor([1.0, -2.0], dtype=torch.float64))
+    idle = torch.nn.Parameter(torch.tensor([3.0], dtype=torch.float64))
+    opt = TF1RMSProp([w, idle], lr=0.1, decay=0.9, momentum=0.5, epsilon=1e-10)
+    g = torch.tensor([0.5, -4.0], dtype=torch.float64)
+    ms, mom, val = np.ones(2), np.zeros(2), np.array([1.0, -2.0])
+    for _ in range(3):
+        w.grad = g.clone(); idle.grad = None
+        opt.step()
+        ms = 0.9 * ms + 0.1 * g.numpy() ** 2
+        mom = 0.5 * mom + 0.1 * g.numpy() / np.sqrt(ms + 1e-10)
+        val = val - mom
+        np.testing.assert_allclose(w.detach().numpy(), val, rtol=1e-14)
+    assert float(idle) == 3.0 and float(opt.state[idle]["ms"]) == 0.9 ** 3          # zero gradient: the slot decays, the variable stays
+    first = 0.1 * 0.5 / np.sqrt(0.9 + 0.1 * 0.25)                                   # torch.optim.RMSprop would start from ms = 0: ~3x larger
+    assert abs(first - 0.0520) < 1e-3
+    v = torch.nn.Parameter(torch.tensor([1.0], dtype=torch.float64))
+    adam = TF1Adam([v], lr=0.01, epsilon=1e-8)
+    m_, v_, x = 0.0, 0.0, 1.0
+    for t in range(1, 4):
+        v.grad = torch.tensor([2.0], dtype=torch.float64)
+        adam.step()
+        m_ = 0.9 * m_ + 0.1 * 2.0; v_ = 0.999 * v_ + 0.001 * 4.0
+        x -= 0.01 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m_ / (np.sqrt(v_) + 1e-8)
+        np.testing.assert_allclose(float(v), x, rtol=1e-14)

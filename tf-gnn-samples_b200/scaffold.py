@@ -24,6 +24,7 @@ from .engine import GraphPlan
 from .gnns import sparse_rgcn_layer
 from .ops import dense as engine_dense
 from .weights import glorot_uniform
+from .tf_optimizers import TF1Adam, TF1RMSProp
 
 _ACT = {"tanh": torch.tanh, "relu": torch.relu, "linear": lambda x: x, None: lambda x: x,
         "elu": torch.nn.functional.elu, "gelu": torch.nn.functional.gelu,
@@ -213,10 +214,10 @@ class RGCNPPIModel(torch.nn.Module):
         if name == "sgd":
             return torch.optim.SGD(self.parameters(), lr=p["learning_rate"])
         if name == "rmsprop":
-            return torch.optim.RMSprop(self.parameters(), lr=p["learning_rate"], alpha=p["learning_rate_decay"],
-                                       momentum=p["momentum"], eps=1e-10)
+            return TF1RMSProp(self.parameters(), lr=p["learning_rate"], decay=p["learning_rate_decay"],
+                              momentum=p["momentum"], epsilon=1e-10)         # the TF 1.13 rule, not torch.optim.RMSprop
         if name == "adam":
-            return torch.optim.Adam(self.parameters(), lr=p["learning_rate"], eps=1e-8)
+            return TF1Adam(self.parameters(), lr=p["learning_rate"], epsilon=1e-8)
         raise Exception('Unknown optimizer "%s".' % p["optimizer"])
 
     def clip_gradients_(self) -> None:
