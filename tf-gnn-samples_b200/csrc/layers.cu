@@ -564,9 +564,11 @@ extern "C" int rgnn_ggnn_forward(const rgnn_plan_t* plan, const float* h, int32_
     s.D = D;
     RGNN_PROPAGATE(transform_sources(plan, ar, cur, D, D, edge_weights, T, stream, s));   // ggnn.py:80-82
     s.agg = aggregation; s.out = m; s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;   // ggnn.py:87-90
-    // GRU on a batch without heavy targets: the edge stage is slabbed together with the cell (below), so that a slab's
-    // aggregated messages are consumed out of L2 by the two cell GEMMs instead of making a round trip through HBM
-    const bool slab_edges = cell_kind == RGNN_CELL_GRU && plan->num_heavy_host == 0 && getenv("RGNN_GRU_SLAB_EDGES_OFF") == nullptr;
+    // Experiment (RGNN_GRU_SLAB_EDGES=1; needs a batch without heavy targets): slab the edge stage together with the cell so
+    // that a slab's aggregated messages are consumed out of L2.  Measured on QM9-10k: 1.975 ms vs 1.928 ms without (job L) --
+    // five small edge-stage launches cost more than the saved round trip of m; off by default.
+    static const bool slab_edges_env = getenv("RGNN_GRU_SLAB_EDGES") != nullptr && atoi(getenv("RGNN_GRU_SLAB_EDGES")) == 1;
+    const bool slab_edges = slab_edges_env && cell_kind == RGNN_CELL_GRU && plan->num_heavy_host == 0;
     if (!slab_edges) RGNN_PROPAGATE(launch_seg_reduce(s, stream));
     GemmParams g;
     g.A1 = m; g.lda1 = D; g.K1 = D;
@@ -699,12 +701,14 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
     s.agg = aggregation;                                                      // :113-116
     s.ln_gamma = ln_gamma + (size_t)t * D; s.ln_beta = ln_beta + (size_t)t * D;   // :120
     s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;
-    // [gamma | beta] = F_l h_v for the wanted target rows (:102), in row slabs small enough (<= 48 MB of gamma / beta rows)
-    // that the edge stage reads them back out of L2: the target-side GEMM and the edge stage alternate per slab.  Needs a
-    // plan without heavy targets (their work lists hold absolute row ids); otherwise one slab = all rows.
+    // [gamma | beta] = F_l h_v for the wanted target rows (:102).  Experiment (RGNN_FILM_SLAB=1; plans without heavy targets):
+    // row slabs small enough (<= 48 MB of gamma / beta rows) that the edge stage reads them back out of L2, target-side GEMM
+    // and edge stage alternating per slab.  Measured on config 5 (50k / 1M): 0.441 ms vs 0.343 ms with ONE slab (job L) -- the
+    // seven short GEMM / edge-stage launch pairs lose more to tails than L2 residency returns; off by default.
     const int Vc = plan->Vt;
     int slab = Vc > 0 ? Vc : 1;
-    if (plan->num_heavy_host == 0 && getenv("RGNN_FILM_SLAB_OFF") == nullptr) {
+    static const bool film_slab_env = getenv("RGNN_FILM_SLAB") != nullptr && atoi(getenv("RGNN_FILM_SLAB")) == 1;
+    if (film_slab_env && plan->num_heavy_host == 0) {
       const long rows_fit = (48L << 20) / ((long)L * 2 * D * (long)sizeof(float));
       const long r = rows_fit / 128 * 128;
       if (r >= 1024 && r < slab) slab = (int)r;
