@@ -320,8 +320,9 @@ def sharded_block(dev, rank, world, local_rank, flush, peaks, layers=4, iters=30
     import ref_cases as RC
     D = 128
     out = {"what": "GNN-FiLM VarMisuse-shaped V=50k M=1M L=6 hidden=128 (BASELINE config 5), ONE graph node-range sharded over %d GPUs "
-                   "(strong scaling); exchange = rgnn_halo_exchange: one pull kernel per layer over CUDA-IPC peer memory (NVLink), "
-                   "cross-rank barrier inside the kernel; no NCCL call on the data path" % world,
+                   "(strong scaling); exchange = rgnn_halo_exchange_overlapped: one pull kernel per layer over CUDA-IPC peer memory (NVLink), "
+                   "cross-rank barrier inside the kernel, forked onto a side stream and joined after the layer's target-side GEMM; "
+                   "no NCCL call on the data path" % world,
            "limiting_step": "halo_pull_kernel (peer reads over NVLink) + the per-rank source transform, which covers every local row "
                             "(owned + halo) unless the compact (source, type) table applies", "variants": []}
 
@@ -345,7 +346,7 @@ def sharded_block(dev, rank, world, local_rank, flush, peaks, layers=4, iters=30
 
         def stack(k):
             for t in range(k):
-                sg.exchange(t % 2)
+                sg.exchange(t % 2, overlap=True)          # joined inside the layer, after its target-side gamma / beta GEMM
                 G.sparse_gnn_film_layer(sg.states(t % 2), sg.plan, cnt, D, weights=ws[t], out=sg.states(1 - t % 2))
 
         # parity of ONE sharded layer (weights of layer 0 = the fixture's) against the reference-generated fixture

@@ -256,6 +256,11 @@ RGNN_API int rgnn_halo_plan_attach(rgnn_halo_plan_t* plan, void* const* peer_sta
  * this buffer are final") as system-scope flags, and keeps its epoch on the device, so a captured CUDA graph can be
  * replayed.  A peer that never arrives faults the kernel after 10 s instead of hanging the GPU. */
 RGNN_API int rgnn_halo_exchange(rgnn_halo_plan_t* plan, int buffer, int32_t d, void* stream);
+/* The same exchange off the caller's critical path: the pull is forked onto a stream of the plan (ordered after everything
+ * enqueued on `stream` so far) and is NOT joined here.  The next rgnn_<x>_forward on rgnn_halo_plan_graph() joins it right
+ * before its first kernel that reads halo rows -- GNN-FiLM runs its target-side gamma / beta GEMM (owned rows only) first, so
+ * that GEMM overlaps the transfer over NVLink.  Capturable into a CUDA graph (fork / join through events). */
+RGNN_API int rgnn_halo_exchange_overlapped(rgnn_halo_plan_t* plan, int buffer, int32_t d, void* stream);
 
 /* CUDA-IPC plumbing for the above (one node): allocate zeroed device memory that peers can map, export its 64-byte handle
  * (ship it with any host-side channel, e.g. torch.distributed.all_gather_object), map a peer's allocation. */

@@ -63,8 +63,8 @@ def test_edges_of_other_ranks_and_bad_ids(cuda_device):
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("world,layers", [(2, 3), (4, 2)])
-def test_virtual_ranks_film_stack_matches_oracle(cuda_device, world, layers):
+@pytest.mark.parametrize("world,layers,overlap", [(2, 3, False), (4, 2, False), (3, 4, True)])
+def test_virtual_ranks_film_stack_matches_oracle(cuda_device, world, layers, overlap):
     """world ranks on one GPU, one stream each: exchange (pull + device barrier) -> FiLM layer -> ... ; the reassembled
     result equals the float64 oracle on the unpartitioned graph, and a second pass (epochs continue) repeats it bit for bit."""
     import torch
@@ -90,7 +90,7 @@ def test_virtual_ranks_film_stack_matches_oracle(cuda_device, world, layers):
         for t in range(layers):
             for g, s, c in zip(graphs, streams, cnts):                 # the ranks' work is enqueued round-robin, runs concurrently
                 with torch.cuda.stream(s):
-                    g.exchange(t % 2)
+                    g.exchange(t % 2, overlap=overlap)   # overlap: pull on a side stream, joined inside the layer call
                     sparse_gnn_film_layer(g.states(t % 2), g.plan, c, D, activation_function="ReLU",
                                           normalize_by_num_incoming=True, weights=wts[t], out=g.states(1 - t % 2))
         torch.cuda.synchronize()
@@ -100,5 +100,57 @@ def test_virtual_ranks_film_stack_matches_oracle(cuda_device, world, layers):
     assert_parity(got, want, "sharded FiLM x%d on %d virtual ranks" % (layers, world), tol=1e-4)
     again = run_once()
     np.testing.assert_array_equal(got, again)
+    for g in graphs:
+        g.close()
+
+
+def test_overlapped_exchange_captured_into_cuda_graphs(cuda_device):
+    """The K-layer sharded sequence with the overlapped exchange (fork onto the plan's side stream, join inside the layer) is
+    recorded into ONE CUDA graph per virtual rank and replayed: the device-side epochs continue across replays, the result
+    equals the float64 oracle every time."""
+    import torch
+    world, layers, D = 2, 2, 64
+    adj, indeg, V = small_graph(seed=9, V=640, M=8000)
+    h = node_states(V, D, seed=4)
+    ws = [W.film_weights(len(adj), D, D, seed=21 + i, random_ln=True) for i in range(layers)]
+    want = h
+    for w in ws:
+        want = R.sparse_gnn_film_layer(want, adj, indeg, D, activation_function="ReLU", normalize_by_num_incoming=False, weights=w)
+    cuts = degree_balanced_cuts(adj, V, world)
+    graphs = [ShardedGraph(adj, cuts, r, world, device=cuda_device) for r in range(world)]
+    ShardedGraph.attach_in_process(graphs, D)
+    streams = [torch.cuda.Stream(device=cuda_device) for _ in range(world)]
+    wts = [W.to_torch(w, cuda_device) for w in ws]
+    cnts = [g.local_num_incoming(indeg) for g in graphs]
+
+    def stack(g, c):
+        for t in range(layers):
+            g.exchange(t % 2, overlap=True)
+            sparse_gnn_film_layer(g.states(t % 2), g.plan, c, D, activation_function="ReLU", weights=wts[t], out=g.states(1 - t % 2))
+
+    def load_inputs():
+        for g in graphs:
+            g.states(0)[: g.n_own] = torch.as_tensor(h[g.lo:g.hi]).to(cuda_device)
+        torch.cuda.synchronize()
+
+    load_inputs()
+    for g, s, c in zip(graphs, streams, cnts):            # eager warm-up (creates the side streams / events, fills caches)
+        with torch.cuda.stream(s):
+            stack(g, c)
+    torch.cuda.synchronize()
+    captured = []
+    for g, s, c in zip(graphs, streams, cnts):            # capture does not execute: the ranks can be recorded one after the other
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg, stream=s):
+            stack(g, c)
+        captured.append(cg)
+    for _ in range(2):
+        load_inputs()
+        for cg, s in zip(captured, streams):
+            with torch.cuda.stream(s):
+                cg.replay()
+        torch.cuda.synchronize()
+        got = np.concatenate([g.states(0)[: g.n_own].cpu().numpy() for g in graphs])   # an even number of layers ends in buffer 0
+        assert_parity(got, want, "overlapped exchange, CUDA-graph replay", tol=1e-4)
     for g in graphs:
         g.close()

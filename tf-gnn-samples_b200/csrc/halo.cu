@@ -41,6 +41,8 @@ struct rgnn_halo_plan {
   float* peer_state[2][RGNN_MAX_WORLD] = {{nullptr}};
   uint32_t* peer_flags[RGNN_MAX_WORLD] = {nullptr};
   bool attached = false;
+  cudaStream_t side = nullptr;         // overlapped exchange: the pull kernel runs here, forked from / joined into the caller's stream
+  cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
   int device = 0;
   cudaStream_t stream = nullptr;
 };
@@ -219,6 +221,9 @@ using namespace rgnn;
 
 extern "C" int rgnn_halo_plan_destroy(rgnn_halo_plan_t* hp) {
   if (hp == nullptr) return RGNN_OK;
+  if (hp->ev_fork != nullptr) cudaEventDestroy(hp->ev_fork);
+  if (hp->ev_done != nullptr) cudaEventDestroy(hp->ev_done);
+  if (hp->side != nullptr) cudaStreamDestroy(hp->side);
   if (hp->graph != nullptr) rgnn_plan_destroy(hp->graph);
   if (hp->block != nullptr) cudaFreeAsync(hp->block, hp->stream);
   delete hp;
@@ -433,8 +438,33 @@ extern "C" int rgnn_halo_plan_attach(rgnn_halo_plan_t* hp, void* const* peer_sta
   return RGNN_OK;
 }
 
+static int halo_exchange_on(rgnn_halo_plan_t* hp, int buffer, int32_t d, cudaStream_t stream);
+
 extern "C" int rgnn_halo_exchange(rgnn_halo_plan_t* hp, int buffer, int32_t d, void* stream_) {
+  return halo_exchange_on(hp, buffer, d, static_cast<cudaStream_t>(stream_));
+}
+
+// The same exchange, off the caller's critical path: forked onto the plan's side stream (after everything enqueued on `stream`
+// so far), NOT joined here -- the next layer forward on rgnn_halo_plan_graph() joins it right before its first kernel that reads
+// halo rows, so the layer's target-side work (FiLM's gamma / beta GEMM over the owned rows) overlaps the pull over NVLink.
+extern "C" int rgnn_halo_exchange_overlapped(rgnn_halo_plan_t* hp, int buffer, int32_t d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RGNN_REQUIRE(hp != nullptr && hp->attached, "halo_exchange_overlapped: plan is NULL / peer memory not attached");
+  if (hp->side == nullptr) {
+    RGNN_CHECK_CUDA(cudaStreamCreateWithFlags(&hp->side, cudaStreamNonBlocking));
+    RGNN_CHECK_CUDA(cudaEventCreateWithFlags(&hp->ev_fork, cudaEventDisableTiming));
+    RGNN_CHECK_CUDA(cudaEventCreateWithFlags(&hp->ev_done, cudaEventDisableTiming));
+  }
+  RGNN_PROPAGATE(plan_wait_sources(hp->graph, stream));        // an unconsumed earlier exchange is joined first
+  RGNN_CHECK_CUDA(cudaEventRecord(hp->ev_fork, stream));
+  RGNN_CHECK_CUDA(cudaStreamWaitEvent(hp->side, hp->ev_fork, 0));
+  RGNN_PROPAGATE(halo_exchange_on(hp, buffer, d, hp->side));
+  RGNN_CHECK_CUDA(cudaEventRecord(hp->ev_done, hp->side));
+  hp->graph->source_ready = hp->ev_done;
+  return RGNN_OK;
+}
+
+static int halo_exchange_on(rgnn_halo_plan_t* hp, int buffer, int32_t d, cudaStream_t stream) {
   RGNN_REQUIRE(hp != nullptr, "halo_exchange: plan is NULL");
   RGNN_REQUIRE(hp->attached, "halo_exchange: peer memory not attached (rgnn_halo_plan_attach)");
   RGNN_REQUIRE(buffer == 0 || buffer == 1, "halo_exchange: buffer %d is not 0 or 1", buffer);

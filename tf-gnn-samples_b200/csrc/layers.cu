@@ -113,6 +113,7 @@ int gemm_shared_a(Arena& ar, const float* A, int V, int K, const float* const* B
 int transform_sources(const rgnn_plan_t* plan, Arena& ar, const float* cur, int d_in, int D, const float* const* W, float* T,
                       cudaStream_t stream, SegParams& s) {
   const int V = plan->V, L = plan->L;
+  RGNN_PROPAGATE(plan_wait_sources(plan, stream));   // an overlapped halo exchange must have landed before source rows are read
   if (plan->n_pairs >= 0 && plan->pair_src != nullptr) {
     GemmParams g;
     g.A1 = cur; g.lda1 = d_in; g.K1 = d_in; g.a_rows = plan->pair_src;
@@ -322,6 +323,7 @@ extern "C" int rgnn_rgcn_forward(const rgnn_plan_t* plan, const float* h, int32_
                                  void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "rgcn"));
+  RGNN_PROPAGATE(plan_wait_sources(plan, stream));
   RGNN_PROPAGATE(check_act(activation, "rgcn"));
   RGNN_PROPAGATE(check_agg(aggregation, "rgcn"));
   RGNN_REQUIRE(edge_weights != nullptr, "rgcn: edge_weights is NULL");
@@ -482,6 +484,7 @@ extern "C" int rgnn_rgdcn_forward(const rgnn_plan_t* plan, const float* h, int32
                                   void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RGNN_PROPAGATE(check_common(plan, h, d, d, out, num_timesteps, "rgdcn"));
+  RGNN_PROPAGATE(plan_wait_sources(plan, stream));
   RGNN_PROPAGATE(check_act(activation, "rgdcn"));
   RGNN_PROPAGATE(check_agg(aggregation, "rgdcn"));
   RGNN_REQUIRE(channel_weights != nullptr, "rgdcn: channel_weights is NULL");
@@ -625,6 +628,7 @@ extern "C" int rgnn_rgat_forward(const rgnn_plan_t* plan, const float* h, int32_
                                  size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "rgat"));
+  RGNN_PROPAGATE(plan_wait_sources(plan, stream));
   RGNN_PROPAGATE(check_act(activation, "rgat"));
   RGNN_REQUIRE(edge_weights != nullptr && attention != nullptr, "rgat: NULL weight table");
   RGNN_REQUIRE(num_heads >= 1 && (d_out % num_heads) == 0, "rgat: state_dim %d not divisible by num_heads %d", d_out, num_heads);
@@ -691,16 +695,6 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
   int din = d_in;
   for (int t = 0; t < num_timesteps; ++t) {                                   // gnn_film.py:85
     float* dst = (t == num_timesteps - 1) ? out : buf[t & 1];
-    SegParams s;
-    seg_from_plan(s, plan);
-    s.D = D;
-    RGNN_PROPAGATE(transform_sources(plan, ar, cur, din, D, edge_weights, T, stream, s));                        // :94 on nodes
-    s.num_incoming = normalize ? num_incoming : nullptr;                      // :96-100
-    s.msg_mode = MSG_FILM; s.mod_stride_node = (long)L * 2 * D; s.mod_stride_type = 2 * D;                        // :103-108
-    s.act_msg = activation;                                                   // :112 (before the sum)
-    s.agg = aggregation;                                                      // :113-116
-    s.ln_gamma = ln_gamma + (size_t)t * D; s.ln_beta = ln_beta + (size_t)t * D;   // :120
-    s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;
     // [gamma | beta] = F_l h_v for the wanted target rows (:102).  Experiment (RGNN_FILM_SLAB=1; plans without heavy targets):
     // row slabs small enough (<= 48 MB of gamma / beta rows) that the edge stage reads them back out of L2, target-side GEMM
     // and edge stage alternating per slab.  Measured on config 5 (50k / 1M): 0.441 ms vs 0.343 ms with ONE slab (job L) -- the
@@ -713,9 +707,24 @@ extern "C" int rgnn_film_forward(const rgnn_plan_t* plan, const float* h, int32_
       const long r = rows_fit / 128 * 128;
       if (r >= 1024 && r < slab) slab = (int)r;
     }
+    // One slab (the default): the target-side GEMM goes FIRST -- it reads owned rows only, so on a sharded plan it overlaps a
+    // pending halo exchange (rgnn_halo_exchange_overlapped), which transform_sources() below joins before touching halo rows.
+    const bool fw_first = slab >= Vc;
+    if (fw_first && Vc > 0)
+      RGNN_PROPAGATE(gemm_shared_a(ar, cur, Vc, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));
+    SegParams s;
+    seg_from_plan(s, plan);
+    s.D = D;
+    RGNN_PROPAGATE(transform_sources(plan, ar, cur, din, D, edge_weights, T, stream, s));                        // :94 on nodes
+    s.num_incoming = normalize ? num_incoming : nullptr;                      // :96-100
+    s.msg_mode = MSG_FILM; s.mod_stride_node = (long)L * 2 * D; s.mod_stride_type = 2 * D;                        // :103-108
+    s.act_msg = activation;                                                   // :112 (before the sum)
+    s.agg = aggregation;                                                      // :113-116
+    s.ln_gamma = ln_gamma + (size_t)t * D; s.ln_beta = ln_beta + (size_t)t * D;   // :120
+    s.ld_out = D; s.heavy_scratch = heavy.heavy_scratch;
     for (int r0 = 0; r0 < Vc; r0 += slab) {
       const int rows = (Vc - r0 < slab) ? Vc - r0 : slab;
-      RGNN_PROPAGATE(gemm_shared_a(ar, cur + (size_t)r0 * din, rows, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));
+      if (!fw_first) RGNN_PROPAGATE(gemm_shared_a(ar, cur + (size_t)r0 * din, rows, din, film_weights, L, 2 * D, 2 * D, FW, RGNN_ACT_LINEAR, stream));
       SegParams q = s;
       q.V = rows; q.seg_off = s.seg_off + r0; q.mod_table = FW;             // FW holds this slab's rows from row 0
       if (q.num_incoming != nullptr) q.num_incoming = s.num_incoming + r0;    // c[type, v] = base[type * ld + v]
@@ -738,6 +747,7 @@ extern "C" int rgnn_edge_mlp_forward(const rgnn_plan_t* plan, const float* h, in
                                      size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "gnn_edge_mlp"));
+  RGNN_PROPAGATE(plan_wait_sources(plan, stream));
   RGNN_PROPAGATE(check_act(activation, "gnn_edge_mlp"));
   RGNN_PROPAGATE(check_agg(aggregation, "gnn_edge_mlp"));
   RGNN_REQUIRE(mlp_kernels && mlp_dims && ln_gamma && ln_beta, "gnn_edge_mlp: NULL weight pointer");
@@ -783,6 +793,7 @@ extern "C" int rgnn_rgin_forward(const rgnn_plan_t* plan, const float* h, int32_
                                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RGNN_PROPAGATE(check_common(plan, h, d_in, d_out, out, num_timesteps, "rgin"));
+  RGNN_PROPAGATE(plan_wait_sources(plan, stream));
   RGNN_PROPAGATE(check_act(activation, "rgin"));
   RGNN_PROPAGATE(check_agg(aggregation, "rgin"));
   RGNN_REQUIRE(ln_gamma && ln_beta, "rgin: NULL layer-norm parameters");

@@ -46,6 +46,9 @@ struct rgnn_plan {
   int num_heavy_items_host = -1;    // host copy of flags[3] once rgnn_plan_status has read it
   int num_heavy_host = -1;          // host copy of flags[1] once rgnn_plan_status has read it, else -1
   int* err_flag = nullptr;          // device flags: [0] out-of-range node id seen, [1] number of heavy targets, [2] heavy (source,type) pairs      // device flag: an adjacency list held an out-of-range node id
+  // Set by rgnn_halo_exchange_overlapped: rows >= Vt (the halo) become valid when this event fires.  The next layer forward
+  // makes its stream wait for it right before the first kernel that reads halo rows (after the target-side work) and clears it.
+  mutable cudaEvent_t source_ready = nullptr;
   void* block = nullptr;        // the one pool allocation behind all arrays above
   cudaStream_t stream = nullptr; // creation stream (the block is freed stream-ordered on it)
 };
@@ -53,6 +56,15 @@ struct rgnn_plan {
 namespace rgnn {
 // Build plan->rev_* on `stream` if absent (not thread-safe; called by the first backward on this plan).
 int plan_ensure_reverse(rgnn_plan* plan, cudaStream_t stream);
+// make `stream` wait for a pending overlapped halo exchange (no-op otherwise)
+inline int plan_wait_sources(const rgnn_plan* plan, cudaStream_t stream) {
+  if (plan->source_ready != nullptr) {
+    const cudaError_t e = cudaStreamWaitEvent(stream, plan->source_ready, 0);
+    plan->source_ready = nullptr;
+    if (e != cudaSuccess) { set_error("CUDA error %s waiting for the halo exchange: %s", cudaGetErrorName(e), cudaGetErrorString(e)); return RGNN_E_CUDA; }
+  }
+  return RGNN_OK;
+}
 constexpr int RGNN_HEAVY_SEGMENT = 512;
 constexpr int RGNN_HEAVY_CHUNK = 256;     // edges per work item of a split heavy target (one CTA each)
 }  // namespace rgnn

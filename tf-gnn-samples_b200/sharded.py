@@ -211,10 +211,14 @@ class ShardedGraph:
             raise RgnnError(RGNN_E_INVALID, "ShardedGraph.attach(state_dim) has not been called")
         return self._states[buffer]
 
-    def exchange(self, buffer: int):
-        """Refresh the halo rows of state buffer ``buffer`` from their owners (rgnn_halo_exchange).  Collective."""
+    def exchange(self, buffer: int, overlap: bool = False):
+        """Refresh the halo rows of state buffer ``buffer`` from their owners (rgnn_halo_exchange).  Collective.
+        ``overlap=True`` (rgnn_halo_exchange_overlapped): the pull runs on a side stream and is joined by the next layer call
+        on ``self.plan`` right before it reads halo rows -- the layer's target-side work overlaps the transfer."""
+        lib = load_library()
+        fn = lib.rgnn_halo_exchange_overlapped if overlap else lib.rgnn_halo_exchange
         with torch.cuda.device(self.device):
-            check(load_library().rgnn_halo_exchange(self.handle, int(buffer), int(self.state_dim or 0), current_stream_ptr(self.device)))
+            check(fn(self.handle, int(buffer), int(self.state_dim or 0), current_stream_ptr(self.device)))
 
     def halo_bytes(self) -> int:
         return self.n_halo * (self.state_dim or 0) * 4
