@@ -929,7 +929,9 @@ static void launch_seg_pair(const SegParams& p, dim3 grid, cudaStream_t stream) 
   launch_pdl(seg_reduce_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
   count_launch();
   if (p.heavy_threshold > 0 && p.heavy_known != 0) {   // unknown (-1) or > 0: a few persistent CTAs walk the heavy list
-    if (p.heavy_scratch != nullptr && p.heavy_items != nullptr) {   // multi-CTA split: partial rows per work item, then one warp per target
+    // multi-CTA split (partial rows per work item, then one warp per target) when the plan is KNOWN to hold heavy targets; with
+    // an unread count (deferred validation) one launch of the one-CTA-per-target kernel walks the -- usually empty -- list
+    if (p.heavy_known > 0 && p.heavy_scratch != nullptr && p.heavy_items != nullptr) {
       const unsigned ix = p.heavy_items_known > 0 ? (unsigned)(p.heavy_items_known < 1184 ? p.heavy_items_known : 1184) : 296u;
       seg_reduce_heavy_part_kernel<NV, MODE, MAXAGG, SCALED, ACTMSG><<<dim3(ix, grid.y), WARPS_PER_BLOCK * 32, 0, stream>>>(p);
       const unsigned fx = p.heavy_known > 0 ? (unsigned)((p.heavy_known + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK) : 148u;
@@ -1025,7 +1027,7 @@ int launch_seg_reduce(const SegParams& p, cudaStream_t stream) {
       if (p.num_incoming != nullptr) launch_pdl(seg_reduce_half_kernel<true>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
       else launch_pdl(seg_reduce_half_kernel<false>, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, p);
       count_launch();
-      if (p.heavy_threshold > 0 && p.heavy_known != 0 && p.heavy_scratch != nullptr && p.heavy_items != nullptr) {
+      if (p.heavy_threshold > 0 && p.heavy_known > 0 && p.heavy_scratch != nullptr && p.heavy_items != nullptr) {
         const dim3 g128(1, (p.D + 127) / 128);
         const unsigned ix = p.heavy_items_known > 0 ? (unsigned)(p.heavy_items_known < 1184 ? p.heavy_items_known : 1184) : 296u;
         const unsigned fx = p.heavy_known > 0 ? (unsigned)((p.heavy_known + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK) : 148u;
