@@ -115,7 +115,10 @@ RGNN_API int rgnn_plan_export(const rgnn_plan_t* plan, int32_t* seg_off, int32_t
  * weights as pre-swizzled TF32 hi/lo shared-memory images; normally they are rebuilt from the caller's
  * kernels on every forward.  With the cache on, images are built once per distinct (weight pointers,
  * shape, tiling) and reused; the caller must call rgnn_weight_cache_clear() after changing cached weights
- * in place.  A cache miss inside CUDA-graph capture is an error (run the layer once eagerly first). */
+ * in place.  A cache miss inside CUDA-graph capture is an error (run the layer once eagerly first).
+ * The key holds device ADDRESSES, not contents: a caller that frees a cached weight and later receives the same address for a
+ * different weight (a new model in the same process) must call rgnn_weight_cache_clear() in between, or the old images are
+ * used silently.  The Python binding does this itself (it tracks the owning tensor's lifetime and version per address). */
 RGNN_API int rgnn_set_weight_cache(int enable);
 RGNN_API int rgnn_weight_cache_clear(void);
 

@@ -138,16 +138,23 @@ class NodeRangePartition:
         # rank, so no handshake is needed.
         owner = np.searchsorted(self.cuts, remote, side="right") - 1
         self.recv_counts = np.bincount(owner, minlength=world_size).astype(np.int64)
-        self.send_local_idx: List[np.ndarray] = []
-        for p in range(world_size):
-            if p == rank:
-                self.send_local_idx.append(np.zeros(0, np.int64))
-                continue
-            plo, phi = int(self.cuts[p]), int(self.cuts[p + 1])
-            need = [a[(a[:, 1] >= plo) & (a[:, 1] < phi), 0] for a in adj]
-            need = np.unique(np.concatenate(need)) if need else np.zeros(0, np.int64)
-            need = need[(need >= self.lo) & (need < self.hi)]
-            self.send_local_idx.append(need - self.lo)
+        # What every peer's halo needs from my range: ONE pass over the edges whose source I own (round 1 looped over the
+        # peers and ran np.unique over all edges for each: O(world * M)).  Key = (owner of the target, source): unique keys,
+        # sorted, are exactly the peers' need lists in peer order, each sorted by node id -- the order the receivers expect.
+        self.send_local_idx: List[np.ndarray] = [np.zeros(0, np.int64) for _ in range(world_size)]
+        if adj:
+            src_all = np.concatenate([a[:, 0] for a in adj])
+            tgt_all = np.concatenate([a[:, 1] for a in adj])
+            mine_src = (src_all >= self.lo) & (src_all < self.hi)
+            peer = np.searchsorted(self.cuts, tgt_all[mine_src], side="right") - 1
+            srcs = src_all[mine_src]
+            away = peer != rank
+            keys = np.unique(peer[away].astype(np.int64) * np.int64(max(num_nodes, 1)) + srcs[away])
+            peers_of_keys = keys // np.int64(max(num_nodes, 1))
+            bounds = np.searchsorted(peers_of_keys, np.arange(world_size + 1))
+            for p in range(world_size):
+                if p != rank:
+                    self.send_local_idx[p] = keys[bounds[p]:bounds[p + 1]] % np.int64(max(num_nodes, 1)) - self.lo
         self.send_counts = np.array([x.shape[0] for x in self.send_local_idx], dtype=np.int64)
         self._idx_cache = {}
         self._any_halo = None
