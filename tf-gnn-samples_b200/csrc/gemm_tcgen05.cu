@@ -73,6 +73,11 @@ struct PackParams {
 
 // grid = (k-chunks, n-tiles, BN/32 row slices... ceil), block = 256 threads = 32 image rows x 8 16-byte chunks
 __global__ void __launch_bounds__(256) pack_b_kernel(const __grid_constant__ PackParams p) {
+  // Programmatic dependent launch: the image buffer may still be read by the GEMM enqueued before (the layers reuse one scratch
+  // region), so nothing is written before the predecessor has completed; the GEMM that consumes these images may start its
+  // set-up (barrier init, TMEM allocation) right away -- it waits for this grid before touching them.
+  pdl_wait();
+  pdl_launch_dependents();
   const int chunk = blockIdx.x;           // k-chunk over both segments
   const int tile = blockIdx.y;            // n-tile
   const int nchunks = p.chunks1 + p.chunks2;
@@ -687,7 +692,7 @@ int launch_gemm_tcgen05(const GemmParams& g, void* pack_ws, size_t pack_ws_bytes
       RGNN_REQUIRE(q.b1[j] != nullptr && (g.K2 == 0 || q.b2[j] != nullptr), "gemm: weight pointer %d is NULL", j);
     }
     q.out = static_cast<float*>(pack_ws) + (size_t)zz * p.packed_stride;
-    pack_b_kernel<<<dim3(nchunks, n_tiles, (p.BN + 31) / 32), 256, 0, stream>>>(q);
+    RGNN_CHECK_CUDA(launch_pdl(pack_b_kernel, dim3(nchunks, n_tiles, (p.BN + 31) / 32), dim3(256), 0, stream, q));
     RGNN_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
