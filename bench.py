@@ -562,6 +562,7 @@ def run_ours(args, rank, world, local_rank):
     if args.skip_e2e:
         if rank == 0:
             emit({"metric": METRIC, "value": value, "ms_per_step": ms_per_step, "layer_ms": layer_ms,
+                  "uncached_weights_ms_per_step": uncached_ms,
                   "warm_l2_ms_per_step": warm_ms, "note": "profiling run (--skip-e2e): not a bench line"})
         return
     # One pinned staging buffer holds the step's host inputs back to back (features | adjacency lists |
