@@ -124,3 +124,54 @@ def test_split_tf32_is_exact_and_three_products_recover_fp32_accuracy():
     assert rel.max() < 2e-6                                                                             # vs ~5e-4 for one TF32 product
     one_pass = np.abs(xh.astype(np.float64) * yh - exact) / np.abs(exact).max()
     assert one_pass.max() > 1e-4
+
+
+def packed_image_offset(BN, nl, c16):
+    """pack_b_kernel: float index of the 16-byte chunk c16 of weight row nl (a column of B) inside one hi (or lo) image of BN rows."""
+    return ((nl >> 3) * 256 + (nl & 7) * 32 + ((c16 ^ (nl & 7)) << 2)) * 4
+
+
+def test_cta_pair_weight_halves_are_contiguous_swizzle_atoms():
+    """gemm_tcgen05_kernel<PAIR>: CTA r bulk-copies bytes [r * BN/2 * 128, +BN/2 * 128) of the hi image and of the lo image into
+    ITS stage.  For that to be a valid K-major SWIZZLE_128B operand of BN/2 rows the half must (a) hold exactly the rows
+    [r BN/2, (r+1) BN/2) and nothing else, and (b) keep every row's swizzle phase (row & 7) -- i.e. start on an 8-row atom."""
+    for BN in range(32, 257, 32):
+        half_rows, half_bytes = BN // 2, (BN // 2) * 128
+        assert half_rows % 8 == 0                                   # whole 8-row / 1024-byte swizzle atoms (SBO = 1024)
+        for r in (0, 1):
+            for nl in range(r * half_rows, (r + 1) * half_rows):
+                for c16 in range(8):
+                    off = packed_image_offset(BN, nl, c16)
+                    assert r * half_bytes <= off < (r + 1) * half_bytes           # (a) the row lives in this CTA's byte range
+                    local = off - r * half_bytes                                 # where it lands in the CTA's own image
+                    ln = nl - r * half_rows                                      # its row index in the half-height operand
+                    assert local == sw128_offset(ln, c16)                        # (b) same layout as a BN/2-row image built directly
+
+
+def test_pair_mode_shrinks_the_stage_so_that_a_third_ring_stage_fits():
+    ring_budget = 227 * 1024 - 1024 - 18432 - 512                   # TC_RING_BUDGET of gemm_tcgen05.cu
+    stage = lambda bn, pair: 2 * 128 * 128 + 2 * (bn // 2 if pair else bn) * 128   # noqa: E731
+    assert min(4, ring_budget // stage(256, False)) == 2 and min(4, ring_budget // stage(256, True)) == 3
+    assert min(4, ring_budget // stage(128, False)) == 3 and min(4, ring_budget // stage(128, True)) == 4
+
+
+def test_producer_groups_never_exceed_ring_stages():
+    """Why ngroups = min(TC_GROUPS, S): a group that published chunk q waits for the stage of chunk q + G.  The 'empty' barrier
+    of that stage has completed the phases of all chunks <= the last one consumed; the consumer is at least at chunk q - S
+    (the group could publish q).  The awaited phase is the one of chunk q + G - S; with G > S the barrier can still be two or
+    more phases behind it, and a parity wait (1 bit) cannot distinguish 'two behind' from 'done'."""
+    def phases_behind(G, S):
+        worst = 0
+        for q in range(S, 6 * S * G):
+            awaited = (q + G - S) // S                      # use index (phase) of chunk q + G - S in its stage
+            stage = (q + G) % S
+            consumed_up_to = q - S                          # the consumer has at least finished chunk q - S
+            done = max((c // S for c in range(stage, consumed_up_to + 1, S)), default=-1)   # last completed phase of that stage
+            worst = max(worst, awaited - done)
+        return worst
+    for S in (2, 3, 4):
+        for G in (1, 2, 3, 4):
+            if G <= S:
+                assert phases_behind(G, S) <= 1, (G, S)     # waiting for the very next phase: parity is unambiguous
+            else:
+                assert phases_behind(G, S) >= 2, (G, S)     # the bug of the first 3-group build (job C)

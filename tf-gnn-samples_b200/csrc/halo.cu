@@ -441,7 +441,11 @@ extern "C" int rgnn_halo_plan_attach(rgnn_halo_plan_t* hp, void* const* peer_sta
 static int halo_exchange_on(rgnn_halo_plan_t* hp, int buffer, int32_t d, cudaStream_t stream);
 
 extern "C" int rgnn_halo_exchange(rgnn_halo_plan_t* hp, int buffer, int32_t d, void* stream_) {
-  return halo_exchange_on(hp, buffer, d, static_cast<cudaStream_t>(stream_));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // two exchange kernels of one plan must never run concurrently (they share the epoch / ticket counters): an overlapped
+  // exchange that no layer forward has joined yet is joined here first
+  if (hp != nullptr && hp->graph != nullptr) RGNN_PROPAGATE(plan_wait_sources(hp->graph, stream));
+  return halo_exchange_on(hp, buffer, d, stream);
 }
 
 // The same exchange, off the caller's critical path: forked onto the plan's side stream (after everything enqueued on `stream`
