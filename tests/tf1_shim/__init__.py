@@ -21,6 +21,7 @@ Tensors are numpy arrays; every op runs immediately.  Variables are created on f
 """
 import contextlib
 import math
+import os
 import sys
 import types
 from typing import Callable, Dict, List, Optional
@@ -353,13 +354,78 @@ def build_modules(session: Session):
 
     tfutils.unsorted_segment_log_softmax = unsorted_segment_log_softmax
     dpu.tfutils = tfutils
+
+    class _Placeholder:
+        """tf.placeholder: only ever used as a feed_dict KEY by the reference's batchers (tasks/*_task.py
+        make_minibatch_iterator); hashable by identity like a tf.Tensor."""
+
+        def __init__(self, dtype, shape=None, name=None):
+            self.dtype, self.shape, self.name = dtype, shape, name
+
+        def __repr__(self):
+            return "<placeholder %s>" % self.name
+
+    tf.placeholder = _Placeholder
+
+    class RichPath:
+        """dpu_utils.utils.RichPath, local files only: what the reference's loaders call (tasks/qm9_task.py:77-87,
+        tasks/ppi_task.py:85-88) -- join, .path, read_by_file_suffix for .jsonl.gz (generator of records), .json, .npy."""
+
+        def __init__(self, path):
+            self.path = str(path)
+
+        @classmethod
+        def create(cls, path, azure_info_path=None):
+            return cls(path)
+
+        def join(self, filename):
+            return RichPath(os.path.join(self.path, filename))
+
+        def __str__(self):
+            return self.path
+
+        __repr__ = __str__
+
+        def read_by_file_suffix(self):
+            import gzip
+            import json
+            if self.path.endswith(".jsonl.gz"):
+                def records():
+                    with gzip.open(self.path, "rt") as f:
+                        for line in f:
+                            yield json.loads(line)
+                return records()
+            if self.path.endswith(".json"):
+                with open(self.path) as f:
+                    return json.load(f)
+            if self.path.endswith(".npy"):
+                return np.load(self.path)
+            raise ValueError("unsupported suffix: %s" % self.path)
+
+    dpu_utils_utils = types.ModuleType("dpu_utils.utils")
+    dpu_utils_utils.RichPath = RichPath
+    dpu.utils = dpu_utils_utils
     session.tf = tf
-    return {"tensorflow": tf, "tensorflow.nn": nn, "tensorflow.keras": keras, "tensorflow.keras.layers": keras.layers,
+    return {"tensorflow": tf, "dpu_utils.utils": dpu_utils_utils, "tensorflow.nn": nn, "tensorflow.keras": keras, "tensorflow.keras.layers": keras.layers,
             "tensorflow.layers": layers, "tensorflow.contrib": contrib, "tensorflow.contrib.layers": contrib.layers,
             "tensorflow.initializers": initializers, "dpu_utils": dpu, "dpu_utils.tfutils": tfutils}
 
 
-_REFERENCE_MODULES = ("gnns", "utils")
+_REFERENCE_MODULES = ("gnns", "utils", "tasks")
+
+
+def import_reference_task(module: str, reference_root: str = REFERENCE_ROOT):
+    """Import the reference's ``tasks/<module>.py`` inside an ``installed()`` block WITHOUT running tasks/__init__.py (it
+    pulls in the VarMisuse task and with it dpu_utils.codeutils, which the shim does not restate): a bare package object
+    with the right __path__ stands in for it, the submodule itself is the unmodified reference file."""
+    import importlib
+    if "tasks" not in sys.modules:
+        pkg = types.ModuleType("tasks")
+        pkg.__path__ = [os.path.join(reference_root, "tasks")]
+        sys.modules["tasks"] = pkg
+    mod = importlib.import_module("tasks." + module)
+    assert os.path.realpath(mod.__file__).startswith(os.path.realpath(reference_root)), mod.__file__
+    return mod
 
 
 @contextlib.contextmanager

@@ -7,7 +7,7 @@ The reference's datasets are not shipped (data/ppi, data/varmisuse) or not avail
 box (data/qm9), so the generators below produce seeded, shape-matched synthetic graphs
 (SURVEY.md 8d / Appendix B).  Everything here is numpy on the host, like the reference.
 """
-from typing import Dict, List, NamedTuple, Optional, Sequence
+from typing import Dict, Iterator, List, NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -151,7 +151,10 @@ def qm9_graph_to_sample(raw: Dict, num_edge_types: int, add_self_loop_edges: boo
     """One record {"graph": [(src, bond, dst)...], "node_features": [[15 floats]...]} -> per-type adjacency lists and
     in-degrees exactly as __graph_to_adjacency_lists builds them (tasks/qm9_task.py:114-147): bond types start at 1
     (0 is the self-loop type when enabled, else types are shifted down by one); tied directions put (dst, src) in the
-    same type; each list is sorted by (src, dst); untied directions append the reversed lists as extra types."""
+    same type; each list is sorted by (src, dst); untied directions append the reversed lists as extra types.
+    (tie_fwd_bkwd_edges=False cannot actually run in the reference: :139-145 appends to the list it enumerates and raises
+    IndexError on the first molecule -- tests/test_reference_batcher_pin.py.  What is built here is what that loop evidently
+    means, in-degree quirk included; every configuration the reference CAN run is pinned bit-exact by the same test.)"""
     num_nodes = len(raw["node_features"])
     lists: List[List] = [[] for _ in range(num_edge_types)]
     indeg = np.zeros((num_edge_types, num_nodes), dtype=np.float64)
@@ -266,6 +269,21 @@ def pack_batch(graphs: Sequence[GraphSample], max_nodes_per_batch: Optional[int]
                  type_to_num_incoming_edges=np.concatenate(indeg, axis=1).astype(np.float32),
                  num_graphs=len(feats), num_nodes=node_offset, num_edges=num_edges,
                  graph_node_offsets=np.asarray(offsets, dtype=np.int64))
+
+
+def minibatches(graphs: Sequence[GraphSample], max_nodes_per_batch: int) -> Iterator[Tuple[Batch, int]]:
+    """One epoch of minibatches, the outer loop of tasks/ppi_task.py:211-256 (same in qm9_task.py:212-261): pack graphs in
+    order until the next one would reach the node budget, emit, continue with that graph.  Yields (batch, index of its first
+    graph).  A graph with >= max_nodes_per_batch nodes can never be packed -- the reference then spins on an empty batch
+    (np.concatenate of an empty list raises); here it is a ValueError up front."""
+    start = 0
+    while start < len(graphs):
+        n = graphs[start].node_features.shape[0]
+        if not (n < max_nodes_per_batch):
+            raise ValueError("graph %d has %d nodes: does not fit max_nodes_per_batch=%d" % (start, n, max_nodes_per_batch))
+        batch = pack_batch(graphs[start:], max_nodes_per_batch)
+        yield batch, start
+        start += batch.num_graphs
 
 
 def ppi_like_batch(num_graphs: int = 1, num_nodes: int = 2245, num_links: int = 59000, seed: int = 0,
