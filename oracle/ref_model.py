@@ -1,5 +1,9 @@
-"""numpy restatement of the RGCN/PPI whole-model forward (TEST INFRASTRUCTURE; PARITY UNPINNED):
-models/sparse_graph_model.py:162-202 with RGCN_Model's defaults + tasks/ppi_task.py:176-179."""
+"""numpy restatement of the whole-model forward (TEST INFRASTRUCTURE): models/sparse_graph_model.py:162-202, the
+models/<x>_model.py adapters, the PPI head (tasks/ppi_task.py:176-195) and the QM9 head (tasks/qm9_task.py:162-199).
+
+PINNED: tests/test_reference_model_pin.py runs the reference's own scaffold + heads (unmodified, eagerly under
+tests/tf1_shim.graph_mode) for all seven model classes on both tasks and compares final node representations and task metrics
+with this module at 1e-12, the weights taken from the reference's variables by name (fixtures tests/golden/ref_model_*.npz)."""
 import numpy as np
 
 from . import ref_layers as R
@@ -104,3 +108,14 @@ def qm9_metrics(outputs, targets, task_ids):
     m["loss"] = float(sum(np.mean(0.5 * err[i] ** 2) for i in range(err.shape[0])))
     m["total_loss"] = m["loss"] * err.shape[1]
     return m
+
+
+def ppi_metrics(logits, labels):
+    """tasks/ppi_task.py:181-195 + utils/utils.py:61-74: summed sigmoid cross-entropy (max(x,0) - x*z + log(1+exp(-|x|))),
+    loss = total / number of nodes, micro-F1 from integer counts of round(sigmoid(x)) (round-half-even: 0.5 -> 0)."""
+    x, z = np.asarray(logits, np.float64), np.asarray(labels, np.float64)
+    total = float(np.sum(np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))))
+    pred, lab = np.round(1.0 / (1.0 + np.exp(-x))).astype(np.int64), z.astype(np.int64)
+    tp, fp, fn = np.count_nonzero(pred * lab), np.count_nonzero(pred * (lab - 1)), np.count_nonzero((pred - 1) * lab)
+    precision, recall = tp / (tp + fp), tp / (tp + fn)
+    return {"loss": total / x.shape[0], "total_loss": total, "f1_score": float(2 * precision * recall / (precision + recall))}

@@ -1,0 +1,182 @@
+"""SURVEY.md 8f (the scaffold around the hot path): oracle/ref_model.py, checkpoint.py's variable-name sorting and
+SparseGraphModel's snapshot loading against the REFERENCE'S OWN model scaffold and task heads.
+
+models/sparse_graph_model.py + models/<x>_model.py + tasks/{ppi,qm9}_task.py are executed unmodified under
+tests/tf1_shim.graph_mode (placeholders hand out the feed, so the static graph runs eagerly while the constructor builds it;
+only TF kernel semantics are restated).  What comes out -- the variables under the names the reference created them with, the
+pickle its own save_model wrote, final node representations, loss / MAE / micro-F1, the "Model has N parameters." count --
+is committed as tests/golden/ref_model_<case>.npz and compared here:
+
+* everywhere: snapshot -> load_reference_checkpoint -> sort_variables -> oracle whole model on batching.py's feed == the
+  reference's outputs (1e-12); snapshot -> SparseGraphModel.load_reference_weights -> every parameter lands where the
+  oracle reads it; parameter counts equal the reference's;
+* where /root/reference exists: the same against a fresh run (the fixtures are current), default_params of every model
+  class, and README.md:29's 699257 parameters counted by the reference's own loop."""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+for p in (HERE, os.path.join(HERE, "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import batcher_cases as BC      # noqa: E402
+import model_cases as MC        # noqa: E402
+
+checkpoint = importlib.import_module("tf-gnn-samples_b200.checkpoint")
+have_reference = pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference checkout is not on this box")
+ALL = sorted(MC.CASES)
+
+
+def fixture(name):
+    z = np.load(os.path.join(HERE, "golden", "ref_model_%s.npz" % name))
+    snap = checkpoint.load_reference_checkpoint(z["pickle"].tobytes())
+    return z, snap
+
+
+@pytest.fixture(scope="module")
+def ppi_dir(tmp_path_factory):
+    return BC.write_ppi_dir(str(tmp_path_factory.mktemp("ppi")), "test")
+
+
+def repo_feed(case, task_params, ppi_dir):
+    """The case's minibatch from batching.py (bit-identical to the reference batcher's: test_reference_batcher_pin.py)."""
+    if case["task"] == "qm9":
+        feeds, L = BC.repo_qm9_feeds(task_params, case["budget"])
+    else:
+        feeds, L = BC.repo_ppi_feeds(task_params, case["budget"], ppi_dir)
+    return feeds[0], L
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / np.abs(np.asarray(b, np.float64)).max())
+
+
+def check_metrics(got, want, what):
+    assert set(got) == set(want), (what, sorted(got), sorted(want))
+    for k, v in want.items():
+        tol = 1e-6 if k == "f1_score" else 1e-11              # the reference casts F1 to float32 (utils/utils.py:74)
+        assert abs(float(got[k]) - float(v)) <= tol * max(1.0, abs(float(v))), (what, k, float(got[k]), float(v))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_oracle_whole_model_on_the_reference_snapshot(name, ppi_dir):
+    case = MC.CASES[name]
+    z, snap = fixture(name)
+    assert snap.model_class == json.loads(str(z["meta"]))["model"] and snap.task_class == json.loads(str(z["meta"]))["task"]
+    assert sorted(snap.weights) == list(z["variable_names"])
+    feed, L = repo_feed(case, snap.task_params, ppi_dir)
+    assert L == int(z["num_edge_types"]) and int(feed["num_nodes"]) == int(z["num_nodes"])
+    o = MC.run_oracle(case, feed, snap.weights, snap.model_params, snap.task_params, L)
+    assert rel(o["final"], z["final"]) <= 1e-12, name
+    check_metrics(o["metrics"], json.loads(str(z["metrics"])), name)
+    o32 = MC.run_oracle(case, feed, snap.weights, snap.model_params, snap.task_params, L, dtype=np.float32)
+    assert o32["final"].dtype == np.float32 and rel(o32["final"], z["final"]) <= 4 * float(z["err32"]) + 1e-6
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_snapshot_loads_into_the_scaffold_by_variable_name(name, ppi_dir):
+    """Every parameter of SparseGraphModel receives the value the oracle reads for it (same sorted dictionaries), none is left
+    at its initial value, and the parameter count is the one the reference printed."""
+    import torch
+    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    case = MC.CASES[name]
+    z, snap = fixture(name)
+    feed, L = repo_feed(case, snap.task_params, ppi_dir)
+    feature_size = feed["initial_node_features"].shape[1]
+    kw = dict(num_labels=feed["target_labels"].shape[1]) if case["task"] == "ppi" else dict(task_ids=tuple(snap.task_params["task_ids"]))
+    model = scaffold.SparseGraphModel(case["kind"], case["task"], L, feature_size, params=snap.model_params, device="cpu", **kw)
+    assert model.num_parameters() == int(z["num_parameters"])
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    left = model.load_reference_weights(snap.weights)
+    assert left == [], left
+    o = MC.run_oracle(case, feed, snap.weights, snap.model_params, snap.task_params, L)
+
+    def same(dst, src, path):
+        if isinstance(dst, dict):
+            for k, v in dst.items():
+                if k != "kind" and v is not None:
+                    same(v, src[k], path + "." + k)
+        elif isinstance(dst, (list, tuple)):
+            assert len(dst) == len(src), path
+            for i, v in enumerate(dst):
+                same(v, src[i], "%s.%d" % (path, i))
+        else:
+            assert np.array_equal(dst.detach().numpy(), np.asarray(src, np.float32)), path
+
+    for l, w in enumerate(model.layers):
+        same(w, o["layers"][l], "gnn_layer_%d" % l)
+    if model.projection is not None:
+        same(model.projection, o["outside"]["projection"], "projection")
+    if case["task"] == "ppi":
+        same(model.head, [h for h in o["outside"]["head"] if "bias" in h][-1], "head")
+    else:
+        for i, t in enumerate(snap.task_params["task_ids"]):
+            same(model.head[i], o["outside"]["qm9_heads"][t], "out_layer_task%d" % t)
+    untouched = [n for n, p in model.named_parameters() if torch.equal(p, before[n]) and float(p.detach().abs().max()) not in (0.0, 1.0)]
+    assert untouched == [], untouched
+
+
+def test_default_params_of_the_snapshots_are_the_packages():
+    """model_params in the reference's pickle = <X>_Model.default_params() + the case's overrides; scaffold.model_default_params
+    restates those defaults (keys the loops never read -- max_epochs, patience, lr_for_num_graphs_per_batch -- aside)."""
+    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    for name in ALL:
+        case = MC.CASES[name]
+        _, snap = fixture(name)
+        mine = dict(scaffold.model_default_params(case["kind"]), **case["model_params"])
+        for k, v in mine.items():
+            assert snap.model_params[k] == v, (name, k, snap.model_params[k], v)
+        extra = set(snap.model_params) - set(mine)
+        if case["kind"] == "rgdcn":                                # derived in RGDCN_Model.__init__ (rgdcn_model.py:31)
+            assert snap.model_params["channel_dim"] == mine["hidden_size"] // mine["num_channels"]
+            extra -= {"channel_dim"}
+        assert extra <= {"max_epochs", "patience", "lr_for_num_graphs_per_batch"}, name
+
+
+# ---- against a fresh run of the reference (this container) ----
+@have_reference
+@pytest.mark.parametrize("name", ALL)
+def test_fixture_equals_the_reference_scaffold_run_here(name):
+    case = MC.CASES[name]
+    z, snap = fixture(name)
+    r = MC.run_reference(case, np.float64)
+    assert np.array_equal(r["final"], z["final"]) and r["num_parameters"] == int(z["num_parameters"])
+    assert sorted(r["variables"]) == list(z["variable_names"])
+    for k, v in r["variables"].items():
+        assert np.array_equal(np.asarray(v, np.float64), np.asarray(snap.weights[k], np.float64)), k
+    check_metrics({k: float(v) for k, v in r["metrics"].items()}, json.loads(str(z["metrics"])), name)
+    o = MC.run_oracle(case, r["feed"], r["variables"], r["params"], r["task_params"], r["num_edge_types"])
+    assert rel(o["final"], r["final"]) <= 1e-12
+
+
+@have_reference
+def test_readme_parameter_count_by_the_references_own_loop():
+    """README.md:29 'Model has 699257 parameters' (RGCN on PPI: 50 features, 121 labels, 3 edge types, hidden 256, 3 layers),
+    counted by sparse_graph_model.py:153-157 over the variables the reference's scaffold creates -- and by the package."""
+    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    case = dict(kind="rgcn", task="ppi", model_params={"hidden_size": 256, "graph_num_layers": 3}, task_params={}, budget=10 ** 6)
+    r = MC.run_reference(case, np.float32, ppi_kw=dict(feature_dim=50, num_labels=121))
+    assert r["num_parameters"] == 699257
+    assert scaffold.RGCNPPIModel(device="cpu").num_parameters() == 699257
+    assert scaffold.SparseGraphModel("rgcn", "ppi", 3, 50, params=case["model_params"], device="cpu").num_parameters() == 699257
+
+
+@have_reference
+def test_default_params_equal_the_reference_classes():
+    import tf1_shim
+    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    with tf1_shim.installed():
+        tf1_shim.import_reference_task("sparse_graph_task")
+        import models
+        for kind, cls_name in MC.MODEL_CLASSES.items():
+            ref = getattr(models, cls_name).default_params()
+            mine = scaffold.model_default_params(kind)
+            for k, v in mine.items():
+                assert ref[k] == v, (kind, k, ref[k], v)
+            assert set(ref) - set(mine) <= {"max_epochs", "patience", "lr_for_num_graphs_per_batch"}, (kind, set(ref) - set(mine))

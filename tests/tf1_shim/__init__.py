@@ -43,6 +43,8 @@ class Session:
         self.variables: Dict[str, np.ndarray] = {}
         self._uid: Dict[str, int] = {}
         self.tf = None
+        self.feeds: Optional[Dict[str, np.ndarray]] = None     # graph_mode: placeholder name -> value (None: inert placeholders)
+        self.non_trainable = set()
 
     # -- naming (tf.variable_scope(None, default_name=...) / Keras unique layer names) --
     def scope_path(self) -> str:
@@ -307,7 +309,20 @@ def build_modules(session: Session):
 
     keras = types.ModuleType("tensorflow.keras")
     keras.layers = types.ModuleType("tensorflow.keras.layers")
-    keras.layers.Dense = _Dense
+
+    class _KerasDense(_Dense):
+        """tf.keras.layers.Dense: an unnamed Keras layer takes its name at CONSTRUCTION from a per-graph counter that ignores
+        scopes (backend.unique_object_name: dense, dense_1, ...), whereas an unnamed tf.layers.Dense opens
+        variable_scope(None, default_name='dense') at its first call and is numbered within the enclosing scope."""
+
+        def __init__(self, units, activation=None, use_bias=True, kernel_initializer=None, name=None, **kw):
+            if name is None:
+                n = session._uid.get("<keras>/dense", 0)
+                session._uid["<keras>/dense"] = n + 1
+                name = "dense" if n == 0 else "dense_%d" % n
+            super().__init__(units, activation, use_bias, kernel_initializer, name, **kw)
+
+    keras.layers.Dense = _KerasDense
     keras.layers.SimpleRNNCell, keras.layers.GRUCell, keras.layers.LSTMCell = _SimpleRNNCell, _GRUCell, _LSTMCell
     tf.keras = keras
     layers = types.ModuleType("tensorflow.layers")
@@ -355,18 +370,6 @@ def build_modules(session: Session):
     tfutils.unsorted_segment_log_softmax = unsorted_segment_log_softmax
     dpu.tfutils = tfutils
 
-    class _Placeholder:
-        """tf.placeholder: only ever used as a feed_dict KEY by the reference's batchers (tasks/*_task.py
-        make_minibatch_iterator); hashable by identity like a tf.Tensor."""
-
-        def __init__(self, dtype, shape=None, name=None):
-            self.dtype, self.shape, self.name = dtype, shape, name
-
-        def __repr__(self):
-            return "<placeholder %s>" % self.name
-
-    tf.placeholder = _Placeholder
-
     class RichPath:
         """dpu_utils.utils.RichPath, local files only: what the reference's loaders call (tasks/qm9_task.py:77-87,
         tasks/ppi_task.py:85-88) -- join, .path, read_by_file_suffix for .jsonl.gz (generator of records), .json, .npy."""
@@ -402,16 +405,19 @@ def build_modules(session: Session):
                 return np.load(self.path)
             raise ValueError("unsupported suffix: %s" % self.path)
 
+    from . import graph_mode
     dpu_utils_utils = types.ModuleType("dpu_utils.utils")
     dpu_utils_utils.RichPath = RichPath
+    dpu_utils_utils.ThreadedIterator = graph_mode.ThreadedIterator
     dpu.utils = dpu_utils_utils
+    extra = graph_mode.extend(tf, session)       # placeholders, Graph / Session, optimizers, summaries, head ops
     session.tf = tf
-    return {"tensorflow": tf, "dpu_utils.utils": dpu_utils_utils, "tensorflow.nn": nn, "tensorflow.keras": keras, "tensorflow.keras.layers": keras.layers,
+    return {**extra, "tensorflow": tf, "dpu_utils.utils": dpu_utils_utils, "tensorflow.nn": nn, "tensorflow.keras": keras, "tensorflow.keras.layers": keras.layers,
             "tensorflow.layers": layers, "tensorflow.contrib": contrib, "tensorflow.contrib.layers": contrib.layers,
             "tensorflow.initializers": initializers, "dpu_utils": dpu, "dpu_utils.tfutils": tfutils}
 
 
-_REFERENCE_MODULES = ("gnns", "utils", "tasks")
+_REFERENCE_MODULES = ("gnns", "utils", "tasks", "models")
 
 
 def import_reference_task(module: str, reference_root: str = REFERENCE_ROOT):
@@ -423,6 +429,8 @@ def import_reference_task(module: str, reference_root: str = REFERENCE_ROOT):
         pkg = types.ModuleType("tasks")
         pkg.__path__ = [os.path.join(reference_root, "tasks")]
         sys.modules["tasks"] = pkg
+        base = importlib.import_module("tasks.sparse_graph_task")      # what models/sparse_graph_model.py:12 imports from 'tasks'
+        pkg.Sparse_Graph_Task, pkg.DataFold = base.Sparse_Graph_Task, base.DataFold
     mod = importlib.import_module("tasks." + module)
     assert os.path.realpath(mod.__file__).startswith(os.path.realpath(reference_root)), mod.__file__
     return mod

@@ -12,9 +12,11 @@ opens (``gnn_layer_%i`` models/sparse_graph_model.py:177; ``Edge_%i_Weight`` gnn
 gnn_film.py:73; ``Edge_%i_Attention_Parameters`` rgat.py:76; ``Edge_%i_FiLM_Computations`` gnn_film.py:78;
 ``Edge_%i_MLP`` gnn_edge_mlp.py:77, rgin.py:96; ``Edge_%i_Channel_%i_Weight_Computation`` rgdcn.py:104; ``Aggregation_MLP`` rgin.py:81; ``Dense`` sparse_graph_model.py:199;
 Keras / tf.layers auto-names ``dense``, ``dense_1``, ``LayerNorm``, ``gru_cell``, ``simple_rnn_cell``).  TensorFlow is
-not available in this build environment, so the exact scope PREFIXES are unverified: matching is done
-on the ``gnn_layer_<i>`` component and the components after it, whatever precedes them, and every variable that was
-not recognised is reported instead of being dropped silently.
+not available in this build environment; the names were checked by running the reference's own scaffold, heads and
+``save_model`` under tests/tf1_shim (tests/test_reference_model_pin.py: scopes and explicit layer names are the reference's,
+the auto-numbering is the shim's restatement of TF 1.13's rules).  Matching is done on the ``gnn_layer_<i>`` component and
+the components after it, whatever precedes them, and every variable that was not recognised is reported instead of being
+dropped silently.
 """
 import io
 import pickle
@@ -177,21 +179,34 @@ def split_layer_norms(layer: Dict[str, Any], num_timesteps: int) -> Dict[str, An
     return layer
 
 
+_QM9_HEAD = re.compile(r"(^|/)out_layer_task(\d+)/(regression_gate|regression)/dense/(kernel|bias)$")
+
+
 def scaffold_variables(outside: Dict[str, np.ndarray], feature_size: int, hidden_size: int) -> Dict[str, np.ndarray]:
     """The variables created outside the gnn_layer scopes: the bias-free input projection
     (models/sparse_graph_model.py:166-170, absent when the feature size equals hidden_size) and the task head.
-    For the PPI head (tasks/ppi_task.py:176-179) that is one Dense with bias.  They are Keras auto-named
-    (dense, dense_1, ...) in creation order: projection first."""
+    * PPI head (tasks/ppi_task.py:176-179): one Keras Dense with bias.  Unnamed Keras layers are numbered per graph in
+      creation order (dense, dense_1, ...): the projection, if any, is ``graph_model/dense``, the head the next one.
+    * QM9 head (tasks/qm9_task.py:162-176): per task id ``out_layer_task<id>/regression_gate/dense/{kernel,bias}`` (gate on
+      [h | x0]) and ``out_layer_task<id>/regression/dense/{kernel,bias}`` -> "qm9_heads": {task id: {"gate_kernel",
+      "gate_bias", "kernel", "bias"}}.
+    Names verified against the reference's own scaffold run under tests/tf1_shim (tests/test_reference_model_pin.py)."""
     dense: Dict[int, Dict[str, np.ndarray]] = {}
+    qm9: Dict[int, Dict[str, np.ndarray]] = {}
     rest = {}
     for name, value in outside.items():
-        parts = name.split("/")
+        parts = _strip(name).split("/")
+        qm = _QM9_HEAD.search(_strip(name))
+        if qm:
+            key = ("gate_" if qm.group(3) == "regression_gate" else "") + qm.group(4)
+            qm9.setdefault(int(qm.group(2)), {})[key] = value
+            continue
         ai = _auto_index(parts[-2]) if len(parts) >= 2 else None
         if ai and ai[0] == "dense" and parts[-1] in ("kernel", "bias"):
             dense.setdefault(ai[1], {})[parts[-1]] = value
         else:
             rest[name] = value
-    out: Dict[str, Any] = {"other": rest}
+    out: Dict[str, Any] = {"other": rest, "qm9_heads": qm9}
     order = sorted(dense)
     if feature_size != hidden_size and order:
         first = dense[order[0]]

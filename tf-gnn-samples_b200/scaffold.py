@@ -522,4 +522,9 @@ class SparseGraphModel(torch.nn.Module):
             if not heads:
                 raise KeyError("reference snapshot has no output layer")
             assign(self.head, heads[-1], "head")
+        else:                                                    # out_layer_task<id>/{regression_gate,regression}/dense/*
+            for i, t in enumerate(self.task_ids):
+                if t not in outside["qm9_heads"]:
+                    raise KeyError("reference snapshot has no output layer for task %d" % t)
+                assign(self.head[i], outside["qm9_heads"][t], "out_layer_task%d" % t)
         return list(srt["unused"])
