@@ -73,9 +73,10 @@ def prepare_data_dir(case, data_dir, ppi_kw=None):
         BC.write_ppi_dir(data_dir, "test", **(ppi_kw or {}))
 
 
-def run_reference(case, dtype=np.float64, seed=11, ppi_kw=None):
+def run_reference(case, dtype=np.float64, seed=11, ppi_kw=None, provider=None):
+    """``provider``: explicit variable values by tf name (tf1_shim.variables.provider_from); default: seeded initialisers."""
     import tf1_shim
-    with tempfile.TemporaryDirectory() as tmp, tf1_shim.installed(dtype=dtype, seed=seed) as session:
+    with tempfile.TemporaryDirectory() as tmp, tf1_shim.installed(dtype=dtype, seed=seed, provider=provider) as session:
         prepare_data_dir(case, tmp, ppi_kw)
         task, feed = _first_feed(tf1_shim, case, tmp)
         session.feeds = feed                                        # phase 2: placeholders hand out the feed, the graph runs as it is built

@@ -180,3 +180,97 @@ def test_default_params_equal_the_reference_classes():
             for k, v in mine.items():
                 assert ref[k] == v, (kind, k, ref[k], v)
             assert set(ref) - set(mine) <= {"max_epochs", "patience", "lr_for_num_graphs_per_batch"}, (kind, set(ref) - set(mine))
+
+
+# ---- the export direction: a model of THIS package handed to the reference ----
+EXPORT_CASES = ["rgcn_ppi_scaffold", "film_ppi_scaffold", "rgin_ppi_scaffold", "ggnn_ppi_hidden_is_feature_size",
+                "rgcn_qm9", "ggnn_qm9", "rgat_qm9", "edge_mlp_qm9", "rgdcn_qm9"]
+
+
+def _package_model(case, feed, L, seed):
+    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    params = dict(scaffold.model_default_params(case["kind"]), **case["model_params"], random_seed=seed)
+    task_params = dict({"task_ids": [0]} if case["task"] == "qm9" else {}, **case["task_params"])
+    kw = dict(num_labels=feed["target_labels"].shape[1]) if case["task"] == "ppi" else dict(task_ids=tuple(task_params["task_ids"]))
+    model = scaffold.SparseGraphModel(case["kind"], case["task"], L, feed["initial_node_features"].shape[1], params=params, device="cpu", **kw)
+    import torch
+    with torch.no_grad():                                        # zero / one initial values would hide a swapped bias or gamma
+        for i, (n, p) in enumerate(sorted(model.named_parameters())):
+            if float(p.abs().max()) in (0.0, 1.0):
+                p.add_(0.01 * torch.randn(p.shape, generator=torch.Generator().manual_seed(i)))
+    return model, task_params
+
+
+def to_numpy(obj):
+    if isinstance(obj, dict):
+        return {k: to_numpy(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [to_numpy(v) for v in obj]
+    if obj is None or isinstance(obj, str):
+        return obj
+    return obj.detach().cpu().numpy()
+
+
+@have_reference
+@pytest.mark.parametrize("name", EXPORT_CASES)
+def test_exported_variables_drive_the_reference_scaffold(name, ppi_dir):
+    """SparseGraphModel.to_reference_weights() names every variable the reference's scaffold creates (and nothing else); fed
+    with those values the reference's own forward equals the oracle run on the model's weight dictionaries directly."""
+    from oracle import ref_model
+    from tf1_shim import variables as TV
+    case = MC.CASES[name]
+    task_defaults = {"qm9": {"add_self_loop_edges": True, "tie_fwd_bkwd_edges": True, "task_ids": [0]},
+                     "ppi": {"add_self_loop_edges": True, "tie_fwd_bkwd_edges": False}}[case["task"]]
+    feed, L = repo_feed(case, dict(task_defaults, **case["task_params"]), ppi_dir)
+    model, task_params = _package_model(case, feed, L, seed=5)
+    named = model.to_reference_weights()
+    counter = named.pop("total_num_graphs:0")
+    assert counter.dtype == np.int64 and counter.shape == ()
+    provider = TV.provider_from(named)
+    r = MC.run_reference(case, np.float64, provider=provider)
+    assert provider.used == set(named), sorted(set(named) - provider.used)
+    assert set(r["variables"]) == set(named) | {"total_num_graphs:0"}
+    assert r["num_parameters"] == model.num_parameters()
+    feats = np.asarray(feed["initial_node_features"], np.float32).astype(np.float64)
+    adj = MC.adjacency_of(feed, L)
+    indeg = np.asarray(feed["type_to_num_incoming_edges"], np.float32).astype(np.float64)
+    final = ref_model.node_representations(model.kind, feats, adj, indeg, model.params, to_numpy(model.projection), to_numpy(model.layers))
+    assert rel(final, r["final"]) <= 1e-12
+    if case["task"] == "ppi":
+        head = to_numpy(model.head)
+        want = ref_model.ppi_metrics(final @ head["kernel"].astype(np.float64) + head["bias"], feed["target_labels"])
+    else:
+        outs = ref_model.qm9_outputs(final, feats, feed["graph_nodes_list"], int(feed["num_graphs"]), to_numpy(model.head))
+        want = ref_model.qm9_metrics(outs, np.asarray(feed["target_values"]).astype(np.float32), task_params["task_ids"])
+    check_metrics(want, {k: float(v) for k, v in r["metrics"].items()}, name)
+
+
+@have_reference
+@pytest.mark.parametrize("name", ["rgin_ppi_scaffold", "edge_mlp_qm9", "ggnn_qm9"])
+def test_the_references_restore_accepts_a_snapshot_written_here(name, ppi_dir, tmp_path, capsys):
+    """utils/model_utils.py:58-77 restore(): class names resolve, the task restores from the metadata, the model builds, and
+    load_weights finds a saved value for EVERY variable and uses EVERY saved value (it prints a line otherwise)."""
+    import tf1_shim
+    case = MC.CASES[name]
+    task_defaults = {"qm9": {"add_self_loop_edges": True, "tie_fwd_bkwd_edges": True, "task_ids": [0]},
+                     "ppi": {"add_self_loop_edges": True, "tie_fwd_bkwd_edges": False}}[case["task"]]
+    task_params = dict(task_defaults, out_layer_dropout_keep_prob=1.0, **case["task_params"])
+    feed, L = repo_feed(case, task_params, ppi_dir)
+    model, _ = _package_model(case, feed, L, seed=9)
+    F = feed["initial_node_features"].shape[1]
+    metadata = {"params": task_params, "num_edge_types": L}
+    metadata.update({"annotation_size": F} if case["task"] == "qm9" else
+                    {"initial_node_feature_size": F, "num_labels": feed["target_labels"].shape[1]})
+    path = str(tmp_path / "snapshot.pickle")
+    model.save_reference_snapshot(path, task_params, metadata)
+    with tf1_shim.installed(dtype=np.float32) as session:
+        session.feeds = dict(feed, out_layer_dropout_keep_prob=1.0)
+        mu = tf1_shim.import_reference_model_utils()
+        restored = mu.restore(path, str(tmp_path), run_id="restored")
+        out = capsys.readouterr().out
+        assert "Loaded model from snapshot" in out
+        assert "Freshly initializing" not in out and "not used by model" not in out, out
+        assert type(restored).__name__ == MC.MODEL_CLASSES[case["kind"]] and restored.task.num_edge_types == L
+        want = model.to_reference_weights()
+        for k, v in session.variables.items():
+            assert np.array_equal(np.asarray(v, np.float64), np.asarray(want[k], np.float64)), k

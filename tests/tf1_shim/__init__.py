@@ -436,6 +436,18 @@ def import_reference_task(module: str, reference_root: str = REFERENCE_ROOT):
     return mod
 
 
+def import_reference_model_utils(reference_root: str = REFERENCE_ROOT):
+    """The reference's utils/model_utils.py (name_to_model_class, name_to_task_class, restore) inside an ``installed()`` block.
+    It imports four task classes from ``tasks``; the two whose modules the shim cannot load (Citation_Network_Task: scipy
+    loaders are fine but unused here; VarMisuse_Task: dpu_utils.codeutils) are present as None."""
+    import importlib
+    qm9, ppi = import_reference_task("qm9_task", reference_root), import_reference_task("ppi_task", reference_root)
+    pkg = sys.modules["tasks"]
+    pkg.QM9_Task, pkg.PPI_Task = qm9.QM9_Task, ppi.PPI_Task
+    pkg.Citation_Network_Task = pkg.VarMisuse_Task = None
+    return importlib.import_module("utils.model_utils")
+
+
 @contextlib.contextmanager
 def installed(dtype=np.float64, seed: int = 0, provider: Optional[Callable] = None, reference_root: str = REFERENCE_ROOT):
     """Install the shim as ``tensorflow`` / ``dpu_utils`` and put the reference on sys.path for the duration of the

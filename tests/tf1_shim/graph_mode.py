@@ -34,6 +34,14 @@ class Variable:
     def get_shape(self):
         return [_Dim(d) for d in self.value().shape]
 
+    def assign(self, value):
+        """variable.assign(value) of load_weights (sparse_graph_model.py:118): shapes must agree, as TF checks."""
+        old, new = self.value(), np.asarray(value)
+        if old.shape != new.shape:
+            raise ValueError("assign to %s: shape %s != %s" % (self.name, new.shape, old.shape))
+        self._session.variables[self.name] = new.astype(old.dtype)
+        return None
+
     def __repr__(self):
         return "<variable %s %s>" % (self.name, self.value().shape)
 

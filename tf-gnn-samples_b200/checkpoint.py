@@ -217,6 +217,67 @@ def scaffold_variables(outside: Dict[str, np.ndarray], feature_size: int, hidden
     return out
 
 
+def _auto_name(base: str, i: int) -> str:
+    return base if i == 0 else "%s_%d" % (base, i)
+
+
+def layer_to_variables(layer: Dict[str, Any], prefix: str) -> Dict[str, Any]:
+    """The opposite of sort_variables for ONE gnn_layer scope: a layer function's ``weights=`` dictionary (plus the
+    scaffold's inter_ln_gamma / inter_ln_beta / inter_dense extras) -> {tf variable name: value}.  The scaffold's LayerNorm
+    is created after the layer function's own per-timestep ones, so it is LayerNorm_<number of own norms> (A.11)."""
+    out: Dict[str, Any] = {}
+    for t, k in enumerate(layer.get("edge_weights") or []):
+        out[prefix + "Edge_%d_Weight/kernel:0" % t] = k
+    for t, a in enumerate(layer.get("attention") or []):
+        out[prefix + "Edge_%d_Attention_Parameters:0" % t] = a
+    for t, k in enumerate(layer.get("film_weights") or []):
+        out[prefix + "Edge_%d_FiLM_Computations/kernel:0" % t] = k
+    for t, kernels in enumerate(layer.get("edge_mlps") or []):
+        for j, k in enumerate(kernels):
+            out[prefix + "Edge_%d_MLP/%s/kernel:0" % (t, _auto_name("dense", j))] = k
+    for j, k in enumerate(layer.get("aggr_mlp") or []):
+        out[prefix + "Aggregation_MLP/%s/kernel:0" % _auto_name("dense", j)] = k
+    for t, per_channel in enumerate(layer.get("channel_weights") or []):
+        for c, k in enumerate(per_channel):
+            out[prefix + "Edge_%d_Channel_%d_Weight_Computation/kernel:0" % (t, c)] = k
+    gammas, betas = list(layer.get("ln_gamma") or []), list(layer.get("ln_beta") or [])
+    if layer.get("inter_ln_gamma") is not None:
+        gammas.append(layer["inter_ln_gamma"])
+        betas.append(layer["inter_ln_beta"])
+    for i, (g, b) in enumerate(zip(gammas, betas)):
+        out[prefix + "%s/gamma:0" % _auto_name("LayerNorm", i)] = g
+        out[prefix + "%s/beta:0" % _auto_name("LayerNorm", i)] = b
+    cell = layer.get("cell")
+    if cell is not None:
+        scope = "gru_cell" if str(cell.get("kind", "gru")).lower() == "gru" else "simple_rnn_cell"
+        for key in ("kernel", "recurrent_kernel", "bias"):
+            out[prefix + "%s/%s:0" % (scope, key)] = cell[key]
+    if layer.get("inter_dense") is not None:
+        out[prefix + "Dense/kernel:0"] = layer["inter_dense"]
+    return out
+
+
+def model_to_variables(projection, layers: List[Dict[str, Any]], task: str, head, task_ids=()) -> Dict[str, Any]:
+    """Whole model -> {tf variable name: value} as Sparse_Graph_Model.save_model would list them: ``graph_model/dense`` (the
+    projection, when there is one), ``graph_model/gnn_layer_<i>/...``, then the head -- PPI: the next unnamed Keras Dense
+    (``dense_1``, or ``dense`` without a projection; tasks/ppi_task.py:176-179); QM9: ``out_layer_task<id>/regression_gate/dense``
+    and ``.../regression/dense`` (tasks/qm9_task.py:162-176)."""
+    out: Dict[str, Any] = {}
+    if projection is not None:
+        out["graph_model/dense/kernel:0"] = projection
+    for i, layer in enumerate(layers):
+        out.update(layer_to_variables(layer, "graph_model/gnn_layer_%d/" % i))
+    if task == "ppi":
+        name = "dense_1" if projection is not None else "dense"
+        out[name + "/kernel:0"], out[name + "/bias:0"] = head["kernel"], head["bias"]
+    else:
+        for hd, t in zip(head, task_ids):
+            p = "out_layer_task%d/" % t
+            out[p + "regression_gate/dense/kernel:0"], out[p + "regression_gate/dense/bias:0"] = hd["gate_kernel"], hd["gate_bias"]
+            out[p + "regression/dense/kernel:0"], out[p + "regression/dense/bias:0"] = hd["kernel"], hd["bias"]
+    return out
+
+
 def rgcn_ppi_reference_names(num_layers: int, num_edge_types: int, has_projection: bool, inter_dense_layers,
                              prefix: str = "") -> Dict[str, str]:
     """Parameter name of RGCNPPIModel -> tf variable name the reference would use (A.11), for writing snapshots."""

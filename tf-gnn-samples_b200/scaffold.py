@@ -480,6 +480,24 @@ class SparseGraphModel(torch.nn.Module):
         return dict(zip(keys, torch.stack([m[k].float() for k in keys]).tolist()))
 
     # ---- reference snapshots ----
+    def to_reference_weights(self) -> Dict[str, np.ndarray]:
+        """{tf variable name: array} as Sparse_Graph_Model.save_model stores it (models/sparse_graph_model.py:91-97): what the
+        reference's restore() / load_weights assigns by name.  Inverse of load_reference_weights."""
+        from .checkpoint import model_to_variables
+        named = model_to_variables(self.projection, self.layers, self.task, self.head, self.task_ids)
+        out = {k: v.detach().cpu().numpy() for k, v in named.items()}
+        out["total_num_graphs:0"] = np.zeros((), np.int64)       # the scaffold's graph counter (:143-148) is a global variable too
+        return out
+
+    def save_reference_snapshot(self, path: str, task_params: Optional[Dict] = None, task_metadata: Optional[Dict] = None) -> None:
+        """Write the pickle of save_model (:98-107): model_class / task_class are the names utils/model_utils.py maps back to
+        classes (RGCN, GGNN, RGAT, RGIN, RGDCN, GNN-Edge-MLP<n>, GNN-FiLM; PPI, QM9)."""
+        from .checkpoint import save_reference_checkpoint
+        names = {"rgcn": "RGCN", "ggnn": "GGNN", "rgat": "RGAT", "rgin": "RGIN", "rgdcn": "RGDCN", "gnn-film": "GNN-FiLM",
+                 "gnn-edge-mlp": "GNN-Edge-MLP%d" % self.params.get("num_edge_hidden_layers", 1)}
+        save_reference_checkpoint(path, names[self.kind], self.task.upper(), self.params, task_params or {},
+                                  self.to_reference_weights(), task_metadata)
+
     def load_reference_weights(self, weights: Dict[str, np.ndarray]) -> List[str]:
         """Assign a reference snapshot by tf variable name (checkpoint.sort_variables); the per-layer dictionaries of
         the snapshot and of this model use the same keys.  Raises when a parameter has no saved value / another shape."""
