@@ -291,18 +291,35 @@ _MODEL_DEFAULTS = {                                            # <X>_Model.defau
               "tie_channel_weights": False, "graph_activation_function": "ReLU", "message_aggregation_function": "sum",
               "graph_inter_layer_norm": True},
 }
-_MODEL_ALIASES = {"rgcn_model": "rgcn", "ggnn_model": "ggnn", "rgat_model": "rgat", "rgin_model": "rgin",
-                  "gnn_edge_mlp": "gnn-edge-mlp", "gnn-edge_mlp": "gnn-edge-mlp", "gnn_edge_mlp_model": "gnn-edge-mlp",
-                  "gnn_film": "gnn-film", "gnn_film_model": "gnn-film", "rgdcn_model": "rgdcn"}
+_MODEL_NAMES = {                                               # name_to_model_class (utils/model_utils.py:31-55): name -> (family, extra params)
+    "ggnn": ("ggnn", {}), "ggnn_model": ("ggnn", {}),
+    "gnn_edge_mlp": ("gnn-edge-mlp", {}), "gnn-edge-mlp": ("gnn-edge-mlp", {}), "gnn_edge_mlp_model": ("gnn-edge-mlp", {}),
+    "gnn_edge_mlp0": ("gnn-edge-mlp", {"num_edge_hidden_layers": 0}), "gnn-edge-mlp0": ("gnn-edge-mlp", {"num_edge_hidden_layers": 0}),
+    "gnn_edge_mlp0_model": ("gnn-edge-mlp", {"num_edge_hidden_layers": 0}),
+    "gnn_edge_mlp1": ("gnn-edge-mlp", {"num_edge_hidden_layers": 1}), "gnn-edge-mlp1": ("gnn-edge-mlp", {"num_edge_hidden_layers": 1}),
+    "gnn_edge_mlp1_model": ("gnn-edge-mlp", {"num_edge_hidden_layers": 1}),
+    "gnn_film": ("gnn-film", {}), "gnn-film": ("gnn-film", {}), "gnn_film_model": ("gnn-film", {}),
+    "rgat": ("rgat", {}), "rgat_model": ("rgat", {}), "rgcn": ("rgcn", {}), "rgcn_model": ("rgcn", {}),
+    "rgdcn": ("rgdcn", {}), "rgdcn_model": ("rgdcn", {}), "rgin": ("rgin", {}), "rgin_model": ("rgin", {}),
+}
+
+
+def resolve_model_name(model: str):
+    """(layer family, extra params) for a model name, case-insensitively, exactly the names name_to_model_class accepts
+    (``gnn_edge_mlp0`` / ``gnn-edge-mlp1`` ... fix num_edge_hidden_layers); ValueError("Unknown model type '<lowered name>'")."""
+    name = model.lower()
+    if name not in _MODEL_NAMES:
+        raise ValueError("Unknown model type '%s'" % name)
+    return _MODEL_NAMES[name]
+
+
 _LAYERS_WITH_OWN_LN = ("rgin", "gnn-edge-mlp", "gnn-film")      # one LayerNorm per timestep inside the layer function
 
 
 def model_default_params(model: str) -> Dict:
     """name_to_model_class(...)[0].default_params() of the reference (utils/model_utils.py:30-55)."""
-    kind = _MODEL_ALIASES.get(model.lower(), model.lower())
-    if kind not in _MODEL_DEFAULTS:
-        raise ValueError("Unknown model type '%s'" % model)
-    return dict(_BASE_DEFAULTS, **_MODEL_DEFAULTS[kind])
+    kind, extra = resolve_model_name(model)
+    return {**_BASE_DEFAULTS, **_MODEL_DEFAULTS[kind], **extra}
 
 
 class SparseGraphModel(torch.nn.Module):
@@ -314,11 +331,11 @@ class SparseGraphModel(torch.nn.Module):
                  num_labels: int = 121, task_ids=(0,), device="cuda"):
         super().__init__()
         from . import weights as W
-        self.kind = _MODEL_ALIASES.get(model.lower(), model.lower())
+        self.kind, _ = resolve_model_name(model)
         self.task = task.lower()
         if self.task not in ("ppi", "qm9"):
             raise ValueError("Unknown task type '%s'" % task)
-        self.params = dict(model_default_params(self.kind), **(params or {}))
+        self.params = dict(model_default_params(model), **(params or {}))
         p = self.params
         H, L, T = p["hidden_size"], num_edge_types, p["graph_num_timesteps_per_layer"]
         self.num_edge_types, self.feature_size, self.task_ids = L, feature_size, tuple(task_ids)
