@@ -289,7 +289,7 @@ def sparse_ggnn_layer(node_embeddings, adjacency_lists, state_dim, num_timesteps
 # --------------------------------------------------------------------------------------
 # gnns/rgat.py:9-141
 # --------------------------------------------------------------------------------------
-def sparse_rgat_layer(node_embeddings, adjacency_lists, state_dim, num_timesteps=1, num_heads=4,
+def sparse_rgat_layer(node_embeddings, adjacency_lists, state_dim, num_heads=4, num_timesteps=1,
                       activation_function="tanh", *, weights: Dict, dtype=np.float64):
     h, adj = _prep(node_embeddings, adjacency_lists, dtype)
     num_nodes = h.shape[0]

@@ -107,3 +107,23 @@ def test_model_names_resolve_like_name_to_model_class(reference):
         for k, v in got[1].items():
             assert want[k] == v, (name, k, want[k], v)
         assert scaffold.resolve_model_name(name)[0] == kinds[cls.__name__], name
+
+
+def test_layer_function_signatures_equal_the_references(reference):
+    """gnns/__init__.py exports seven sparse_<x>_layer functions; the package's take the same positional / keyword parameters in
+    the same order with the same defaults, plus keyword-only extras (weights=, plan=, ...) that the reference cannot know."""
+    import inspect
+    import gnns as ref_gnns                                   # the reference's package (inside the fixture's installed() block)
+    pkg = importlib.import_module("tf-gnn-samples_b200.gnns")
+    names = [n for n in dir(ref_gnns) if n.startswith("sparse_") and n.endswith("_layer")]
+    assert sorted(names) == ["sparse_ggnn_layer", "sparse_gnn_edge_mlp_layer", "sparse_gnn_film_layer", "sparse_rgat_layer",
+                             "sparse_rgcn_layer", "sparse_rgdcn_layer", "sparse_rgin_layer"]
+    for n in names:
+        ref = inspect.signature(getattr(ref_gnns, n)).parameters
+        got = inspect.signature(getattr(pkg, n)).parameters
+        shared = [p for p in got.values() if p.kind != inspect.Parameter.KEYWORD_ONLY]
+        assert [p.name for p in shared] == list(ref), (n, [p.name for p in shared], list(ref))
+        for p in shared:
+            assert p.default == ref[p.name].default, (n, p.name, p.default, ref[p.name].default)
+        extras = [p.name for p in got.values() if p.kind == inspect.Parameter.KEYWORD_ONLY]
+        assert "weights" in extras, (n, extras)

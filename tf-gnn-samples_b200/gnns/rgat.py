@@ -12,8 +12,8 @@ from . import _train
 def sparse_rgat_layer(node_embeddings: torch.Tensor,
                       adjacency_lists,
                       state_dim: Optional[int],
-                      num_timesteps: int = 1,
                       num_heads: int = 4,
+                      num_timesteps: int = 1,
                       activation_function: Optional[str] = "tanh",
                       *, weights: Dict, plan=None) -> torch.Tensor:
     """Relational GAT: per type T_l = H W_l; per edge and head k a LeakyReLU(0.2) logit from the
