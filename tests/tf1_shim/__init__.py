@@ -45,6 +45,7 @@ class Session:
         self.tf = None
         self.feeds: Optional[Dict[str, np.ndarray]] = None     # graph_mode: placeholder name -> value (None: inert placeholders)
         self.non_trainable = set()
+        self.run_hook: Optional[Callable] = None                # graph_mode: scripted sess.run (epoch-loop tests)
 
     # -- naming (tf.variable_scope(None, default_name=...) / Keras unique layer names) --
     def scope_path(self) -> str:

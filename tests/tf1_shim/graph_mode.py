@@ -56,6 +56,18 @@ class Placeholder:
         return "<placeholder %s>" % self.name
 
 
+class FeedArray(np.ndarray):
+    """What an eager placeholder hands out: the fed array, but hashable BY IDENTITY like a tf.Tensor, because the reference's
+    epoch loop uses the model's placeholders as feed_dict keys (sparse_graph_model.py:277-281, tasks/*_task.py batchers)."""
+
+    def __hash__(self):
+        return id(self)
+
+
+def _as_feed(value):
+    return np.asarray(value).view(FeedArray)
+
+
 def _resolve(session, obj):
     """sess.run on an eager world: Variables become their values, containers are walked, arrays pass through."""
     if isinstance(obj, Variable):
@@ -76,13 +88,13 @@ def extend(tf, session):
         value = np.asarray(session.feeds[name])
         if dtype is not None and np.issubdtype(np.dtype(dtype), np.floating):
             # the value an fp32 placeholder receives (rounded to float32), carried in the session's float type (fp64 = truth run)
-            return value.astype(np.dtype(dtype)).astype(session.dtype)
-        return value if dtype is None else value.astype(dtype)
+            return _as_feed(value.astype(np.dtype(dtype)).astype(session.dtype))
+        return _as_feed(value if dtype is None else value.astype(dtype))
 
     def placeholder_with_default(default, shape=None, name=None):
         if session.feeds is not None and name in session.feeds:
-            return session.dtype(session.feeds[name])
-        return session.dtype(default)
+            return _as_feed(session.dtype(session.feeds[name]))
+        return _as_feed(session.dtype(default))
 
     tf.placeholder, tf.placeholder_with_default = placeholder, placeholder_with_default
 
@@ -121,6 +133,10 @@ def extend(tf, session):
             self.graph = graph if graph is not None else Graph()
 
         def run(self, fetches, feed_dict=None):
+            """Everything was computed when the graph was built; ``session.run_hook`` (tests of the epoch loop) may script the
+            per-batch results instead -- it sees the fetches and the feed_dict the reference assembled."""
+            if session.run_hook is not None:
+                return session.run_hook(fetches, feed_dict)
             return _resolve(session, fetches)
 
     class ConfigProto:

@@ -72,7 +72,8 @@ def prefetch(items: Iterable, fn: Callable[[Any], Any] = lambda x: x, max_queue_
 def pretty_print_epoch_task_metrics(task: str, task_metric_results: List[Dict[str, float]], num_graphs: int,
                                     task_ids: Sequence[int] = (0,)) -> str:
     if task.lower() == "ppi":                                                   # tasks/ppi_task.py:262-264
-        return "Avg MicroF1: %.3f" % (np.average([m["f1_score"] for m in task_metric_results]),)
+        # micro_f1 casts to float32 (utils/utils.py:74): the reference averages float32 scalars IN float32
+        return "Avg MicroF1: %.3f" % (np.average(np.asarray([m["f1_score"] for m in task_metric_results], dtype=np.float32)),)
     if task.lower() == "qm9":                                                   # tasks/qm9_task.py:267-282
         maes = {t: sum(m["abs_err_task%i" % t] for m in task_metric_results) / float(num_graphs) for t in task_ids}
         maes_str = " ".join("%i:%.5f" % (t, maes[t]) for t in task_ids)
