@@ -73,13 +73,14 @@ def prepare_data_dir(case, data_dir, ppi_kw=None):
         BC.write_ppi_dir(data_dir, "test", **(ppi_kw or {}))
 
 
-def run_reference(case, dtype=np.float64, seed=11, ppi_kw=None, provider=None):
+def run_reference(case, dtype=np.float64, seed=11, ppi_kw=None, provider=None, gradient_hook=None):
     """``provider``: explicit variable values by tf name (tf1_shim.variables.provider_from); default: seeded initialisers."""
     import tf1_shim
     with tempfile.TemporaryDirectory() as tmp, tf1_shim.installed(dtype=dtype, seed=seed, provider=provider) as session:
         prepare_data_dir(case, tmp, ppi_kw)
         task, feed = _first_feed(tf1_shim, case, tmp)
         session.feeds = feed                                        # phase 2: placeholders hand out the feed, the graph runs as it is built
+        session.gradient_hook = gradient_hook
         import models                                               # the reference's package
         cls = getattr(models, MODEL_CLASSES[case["kind"]])
         params = cls.default_params()
@@ -96,7 +97,9 @@ def run_reference(case, dtype=np.float64, seed=11, ppi_kw=None, provider=None):
                 "final": np.asarray(ops["final_node_representations"]),
                 "metrics": {k: np.asarray(v) for k, v in ops["task_metrics"].items()},
                 "num_parameters": count, "num_edge_types": task.num_edge_types, "pickle": pickled,
-                "model_name": cls.name(params), "task_name": task.name()}
+                "model_name": cls.name(params), "task_name": task.name(),
+                "optimizers": list(session.optimizers), "applied": session.applied,
+                "loss_is_task_loss": session.loss_for_gradients is ops["task_metrics"]["loss"]}
 
 
 def adjacency_of(feed, num_edge_types):

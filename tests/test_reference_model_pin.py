@@ -274,3 +274,61 @@ def test_the_references_restore_accepts_a_snapshot_written_here(name, ppi_dir, t
         want = model.to_reference_weights()
         for k, v in session.variables.items():
             assert np.array_equal(np.asarray(v, np.float64), np.asarray(want[k], np.float64)), k
+
+
+# ---- the train step (sparse_graph_model.py:226-260) ----
+@have_reference
+@pytest.mark.parametrize("optimizer", ["SGD", "RMSProp", "Adam"])
+def test_train_step_construction_and_per_tensor_clipping(optimizer, ppi_dir):
+    """__make_train_step run by the reference with PRESCRIBED gradients: which optimizer it builds with which hyper-parameters,
+    that the differentiated quantity is task_metrics['loss'], and that every gradient is clipped BY ITS OWN norm (tf.clip_by_norm,
+    not a global norm), None gradients passing through -- against scaffold.make_optimizer / clip_gradients_ on the same numbers."""
+    import torch
+    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    tfo = importlib.import_module("tf-gnn-samples_b200.tf_optimizers")
+    hp = {"optimizer": optimizer, "learning_rate": 0.003, "learning_rate_decay": 0.9, "momentum": 0.7, "clamp_gradient_norm": 0.5}
+    case = dict(MC.CASES["film_ppi_scaffold"], model_params=dict(MC.CASES["film_ppi_scaffold"]["model_params"], **hp))
+    rng = np.random.default_rng(8)
+    prescribed = {}
+
+    def gradient_hook(name, shape):
+        if name.endswith("gnn_layer_1/LayerNorm/beta:0"):
+            prescribed[name] = None                               # a variable the loss does not depend on
+        else:                                                    # norms on both sides of the clamp
+            prescribed[name] = rng.standard_normal(shape) * (0.5 / np.sqrt(max(1, int(np.prod(shape))))) * rng.choice([0.2, 3.0])
+        return prescribed[name]
+
+    r = MC.run_reference(case, np.float64, gradient_hook=gradient_hook)
+    assert r["loss_is_task_loss"]
+    (cls_name, kwargs), = r["optimizers"]
+    feed, L = repo_feed(case, {"add_self_loop_edges": True, "tie_fwd_bkwd_edges": True}, ppi_dir)
+    model = scaffold.SparseGraphModel(case["kind"], "ppi", L, feed["initial_node_features"].shape[1], params=r["params"],
+                                      num_labels=feed["target_labels"].shape[1], device="cpu")
+    opt = model.make_optimizer()
+    if optimizer == "SGD":
+        assert cls_name == "GradientDescentOptimizer" and kwargs == {"learning_rate": 0.003}
+        assert isinstance(opt, torch.optim.SGD) and opt.defaults["lr"] == 0.003 and opt.defaults["momentum"] == 0
+    elif optimizer == "RMSProp":
+        assert cls_name == "RMSPropOptimizer" and kwargs == {"learning_rate": 0.003, "decay": 0.9, "momentum": 0.7}
+        assert isinstance(opt, tfo.TF1RMSProp)
+        assert (opt.defaults["lr"], opt.defaults["decay"], opt.defaults["momentum"], opt.defaults["epsilon"]) == (0.003, 0.9, 0.7, 1e-10)
+    else:
+        assert cls_name == "AdamOptimizer" and kwargs == {"learning_rate": 0.003}
+        assert isinstance(opt, tfo.TF1Adam) and opt.defaults["lr"] == 0.003 and opt.defaults["epsilon"] == 1e-8
+    # the package's clipping on the same gradients, parameters matched to variables by the exported names
+    checkpoint_mod = importlib.import_module("tf-gnn-samples_b200.checkpoint")
+    named = checkpoint_mod.model_to_variables(model.projection, model.layers, "ppi", model.head)
+    assert set(named) == set(prescribed)
+    for name, p in named.items():
+        p.grad = None if prescribed[name] is None else torch.as_tensor(prescribed[name], dtype=torch.float64).to(p.dtype)
+    pre = {n: None if p.grad is None else float(p.grad.norm()) for n, p in named.items()}
+    assert min(v for v in pre.values() if v is not None) < 0.5 < max(v for v in pre.values() if v is not None)
+    model.clip_gradients_()
+    applied = dict((n, g) for g, n in r["applied"])
+    assert set(applied) == set(named)
+    for name, p in named.items():
+        if prescribed[name] is None:
+            assert applied[name] is None and p.grad is None
+        else:
+            assert np.allclose(p.grad.numpy(), applied[name], rtol=2e-6, atol=1e-9), name
+            assert float(np.linalg.norm(applied[name])) <= 0.5 * (1 + 1e-12)

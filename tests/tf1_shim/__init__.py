@@ -46,6 +46,8 @@ class Session:
         self.feeds: Optional[Dict[str, np.ndarray]] = None     # graph_mode: placeholder name -> value (None: inert placeholders)
         self.non_trainable = set()
         self.run_hook: Optional[Callable] = None                # graph_mode: scripted sess.run (epoch-loop tests)
+        self.gradient_hook: Optional[Callable] = None           # graph_mode: prescribed gradients (train-step tests)
+        self.optimizers, self.applied, self.loss_for_gradients = [], None, None
 
     # -- naming (tf.variable_scope(None, default_name=...) / Keras unique layer names) --
     def scope_path(self) -> str:

@@ -157,17 +157,28 @@ def extend(tf, session):
     tf.summary = summary
 
     class _Optimizer:
+        """tf.train.*Optimizer: records how it was constructed.  No autodiff here: compute_gradients returns (None, var) pairs --
+        or what ``session.gradient_hook(variable name, shape)`` prescribes (tests of the clipping step) -- and apply_gradients
+        records what it was handed (``session.applied``)."""
+
         def __init__(self, *a, **kw):
-            self.args = kw
+            assert not a, "the reference passes keyword arguments only (sparse_graph_model.py:241-249)"
+            self.kwargs = kw
+            session.optimizers.append((type(self).__name__, kw))
 
         def compute_gradients(self, loss, var_list=None):
-            return [(None, v) for v in (var_list or [])]
+            session.loss_for_gradients = loss
+            hook = session.gradient_hook
+            return [(None if hook is None else hook(v.name, v.value().shape), v) for v in (var_list or [])]
 
         def apply_gradients(self, grads_and_vars, **kw):
+            session.applied = [(g, v.name) for g, v in grads_and_vars]
             return None
 
     train = types.ModuleType("tensorflow.train")
-    train.GradientDescentOptimizer = train.RMSPropOptimizer = train.AdamOptimizer = _Optimizer
+    train.GradientDescentOptimizer = type("GradientDescentOptimizer", (_Optimizer,), {})
+    train.RMSPropOptimizer = type("RMSPropOptimizer", (_Optimizer,), {})
+    train.AdamOptimizer = type("AdamOptimizer", (_Optimizer,), {})
     tf.train = train
 
     # ---- the remaining eager ops of the scaffold / heads ----
