@@ -117,3 +117,64 @@ def test_installed_context_leaves_no_trace():
         assert getattr(shim_tf, "__shim__", False) and session.tf is shim_tf
     after = {k for k in sys.modules if k.split(".")[0] in ("tensorflow", "dpu_utils", "gnns", "utils")}
     assert after == before
+
+
+# ---- graph_mode: the eager stand-ins for the scaffold / heads ----
+def test_sigmoid_cross_entropy_and_clip_by_norm_against_torch(tf):
+    import torch
+    rng = np.random.default_rng(0)
+    x, z = rng.standard_normal((7, 5)) * 6, (rng.random((7, 5)) < 0.4).astype(np.float64)
+    want = torch.nn.functional.binary_cross_entropy_with_logits(torch.as_tensor(x), torch.as_tensor(z), reduction="none").numpy()
+    np.testing.assert_allclose(tf.nn.sigmoid_cross_entropy_with_logits(logits=x, labels=z), want, rtol=1e-13, atol=1e-15)
+    g = rng.standard_normal((4, 3))
+    n = np.linalg.norm(g)
+    np.testing.assert_allclose(tf.clip_by_norm(g, n / 2), g / 2)                    # longer than the clamp: rescaled to it
+    np.testing.assert_array_equal(tf.clip_by_norm(g, 2 * n), g * (2 * n) / (2 * n))  # shorter: t * clip / max(norm, clip) == t
+
+
+def test_placeholders_inert_without_feed_and_eager_with_one(tf):
+    s = tf._session
+    a, b = tf.placeholder(tf.float32, [None, 3], name="x"), tf.placeholder(tf.float32, [None, 3], name="x")
+    assert a is not b and len({a: 1, b: 2}) == 2 and a.name == "x"               # feed_dict keys, hashable by identity
+    s.feeds = {"x": np.array([[0.1, 0.2, 0.3]]), "n": 7}
+    x = tf.placeholder(tf.float32, [None, 3], name="x")
+    assert x.dtype == np.float64 and np.array_equal(x, np.float32([[0.1, 0.2, 0.3]]).astype(np.float64))   # what an fp32 placeholder holds
+    assert np.array_equal(tf.placeholder(tf.int64, [], name="n"), 7) and tf.placeholder(tf.int64, [], name="n").dtype == np.int64
+    assert len({x: 1, tf.placeholder(tf.float32, name="x"): 2}) == 2              # still usable as keys (epoch loop)
+    assert float(tf.placeholder_with_default(1.0, [], name="keep")) == 1.0
+    with pytest.raises(KeyError):
+        tf.placeholder(tf.float32, name="missing")
+
+
+def test_unnamed_keras_dense_numbered_per_graph_tf_layers_dense_per_scope(tf):
+    s = tf._session
+    x = np.ones((2, 3))
+    with tf.variable_scope("graph_model"):
+        tf.keras.layers.Dense(4, use_bias=False)(x)                               # projection (sparse_graph_model.py:166)
+        with tf.variable_scope("A"):
+            tf.layers.Dense(4, use_bias=False)(x)
+            tf.layers.Dense(4, use_bias=False)(x)
+        with tf.variable_scope("B"):
+            tf.layers.Dense(4, use_bias=False)(x)
+    tf.keras.layers.Dense(2)(x)                                                   # PPI head (ppi_task.py:176): the graph's 2nd unnamed Keras layer
+    assert list(s.variables) == ["graph_model/dense/kernel:0", "graph_model/A/dense/kernel:0", "graph_model/A/dense_1/kernel:0",
+                                 "graph_model/B/dense/kernel:0", "dense_1/kernel:0", "dense_1/bias:0"]
+
+
+def test_bookkeeping_variable_collections_and_optimizer_stub(tf):
+    s = tf._session
+    with tf.variable_scope("m"):
+        tf.get_variable("w", shape=(3, 2))
+    tf.get_variable(name="total_num_graphs", shape=(), dtype=tf.int64, initializer=tf.zeros_initializer, trainable=False)
+    assert [v.name for v in tf.trainable_variables()] == ["m/w:0"]
+    assert [d.value for d in tf.trainable_variables()[0].get_shape()] == [3, 2]
+    g = tf.Graph()
+    assert [v.name for v in g.get_collection(tf.GraphKeys.GLOBAL_VARIABLES)] == ["m/w:0", "total_num_graphs:0"]
+    sess = tf.Session(graph=g, config=tf.ConfigProto())
+    out = sess.run({v.name: v for v in g.get_collection(tf.GraphKeys.GLOBAL_VARIABLES)})
+    assert out["total_num_graphs:0"].dtype == np.int64 and out["m/w:0"].shape == (3, 2)
+    opt = tf.train.RMSPropOptimizer(learning_rate=0.1, decay=0.5, momentum=0.2)
+    gv = opt.compute_gradients(np.float64(1.0), var_list=tf.trainable_variables())
+    assert [(g_, v.name) for g_, v in gv] == [(None, "m/w:0")] and s.optimizers == [("RMSPropOptimizer", {"learning_rate": 0.1, "decay": 0.5, "momentum": 0.2})]
+    with pytest.raises(ValueError):
+        tf.trainable_variables()[0].assign(np.zeros((2, 2)))

@@ -1,13 +1,15 @@
-"""A numpy-backed stand-in for the slice of TensorFlow 1.13 / dpu_utils that the reference's layer functions call.
+"""A numpy-backed stand-in for the slice of TensorFlow 1.13 / dpu_utils that the reference calls.
 
-TEST INFRASTRUCTURE (like oracle/): it exists so that the UNMODIFIED reference sources
-``/root/reference/gnns/{rgcn,ggnn,rgat,gnn_film,gnn_edge_mlp,rgin,rgdcn}.py`` and ``utils/utils.py`` can be imported
-and executed in this container (TF1 is not installable: Python 3.12, no network), eagerly, on numpy arrays.  The
-reference-owned logic -- which rows are gathered, which kernel multiplies what, where the normalisation / activation /
-layer norm sit, how heads and timesteps are looped, which variables are created under which names -- then runs
-exactly as written; what this module restates are only the TF / Keras / dpu_utils KERNEL semantics (SURVEY.md
-Appendix A), each cited below.  ``tests/golden/make_ref_fixtures.py`` uses it to produce ``tests/golden/ref_*.npz``;
-``tests/golden/make_tf1_fixtures.py`` produces the same files with a real TensorFlow 1.13 for anyone who has one.
+TEST INFRASTRUCTURE (like oracle/): it exists so that the UNMODIFIED reference sources can be imported and executed in this
+container (TF1 is not installable: Python 3.12, no network), eagerly, on numpy arrays:
+  gnns/{rgcn,ggnn,rgat,gnn_film,gnn_edge_mlp,rgin,rgdcn}.py, utils/utils.py      the layer functions        (this file)
+  tasks/{sparse_graph,qm9,ppi}_task.py                                            loaders, batchers, heads   (+ graph_mode.py)
+  models/sparse_graph_model.py, models/*_model.py, utils/model_utils.py           scaffold, train step, epoch loop, save / restore
+The reference-owned logic -- which rows are gathered, which kernel multiplies what, where the normalisation / activation /
+layer norm sit, how heads, timesteps, layers and epochs are looped, which variables are created under which names, what is
+logged -- then runs exactly as written; what this package restates are only the TF / Keras / dpu_utils KERNEL semantics
+(SURVEY.md Appendix A), each cited where it is defined.  ``tests/golden/make_*_fixtures.py`` use it to produce the committed
+fixtures; ``tests/golden/make_tf1_fixtures.py`` produces the layer fixtures with a real TensorFlow 1.13 for anyone who has one.
 
 Usage:
     with tf1_shim.installed(dtype=np.float64, seed=0) as session:
@@ -15,6 +17,7 @@ Usage:
         with session.tf.variable_scope("graph_model"), session.tf.variable_scope("gnn_layer_0"):
             out = sparse_rgcn_layer(h, adjacency_lists, num_incoming, state_dim=D, ...)
         session.variables                              # {"graph_model/gnn_layer_0/Edge_0_Weight/kernel:0": array, ...}
+    (whole models: tests/golden/model_cases.py; batchers: tests/golden/batcher_cases.py; epoch loop: tests/test_reference_training_pin.py)
 
 Tensors are numpy arrays; every op runs immediately.  Variables are created on first use by ``session.provider``
 (default: the Keras / tf.get_variable default initialisers from a seeded generator; tests pass explicit values).
