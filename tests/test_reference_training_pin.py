@@ -33,7 +33,10 @@ PATIENCE, MAX_NODES, SEED = 2, 700, 4
 
 def scripted(task, fold, epoch, step, num_graphs, task_ids):
     """Metrics of batch ``step`` of ``fold`` in ``epoch``: validation improves for three epochs, then gets worse."""
-    quality = [1.0, 0.7, 0.55, 0.6, 0.65, 0.5, 0.4][min(epoch - 1, 6)] if fold == "valid" else 1.0 / epoch
+    if fold == "test":
+        quality = 0.52
+    else:
+        quality = [1.0, 0.7, 0.55, 0.6, 0.65, 0.5, 0.4][min(epoch - 1, 6)] if fold == "valid" else 1.0 / epoch
     loss = quality * (1.0 + 0.01 * step)
     m = {"loss": loss, "total_loss": loss * num_graphs}
     if task == "qm9":
@@ -62,7 +65,7 @@ def write_qm9_folds(d):
     return recs[:150], recs[150:]
 
 
-def run_reference_loop(task_name, data_dir, task_params, model_params, max_nodes=MAX_NODES):
+def run_reference_loop(task_name, data_dir, task_params, model_params, max_nodes=MAX_NODES, test_path=None):
     import tf1_shim
     calls = []
     with tf1_shim.installed(dtype=np.float32) as session:
@@ -90,6 +93,8 @@ def run_reference_loop(task_name, data_dir, task_params, model_params, max_nodes
             if not isinstance(fetches, dict) or "task_metrics" not in fetches:       # save_model's variable fetch
                 return {k: v.value() for k, v in fetches.items()}
             fold = "train" if "train_step" in fetches else "valid"
+            if state["epoch"] == 99:
+                fold = "test"
             if fold != state["fold"]:
                 if fold == "train" and state["fold"] == "valid":
                     state["epoch"] += 1
@@ -107,6 +112,9 @@ def run_reference_loop(task_name, data_dir, task_params, model_params, max_nodes
         sgm.time = types.SimpleNamespace(time=make_counter_clock())   # the module's clock; the source file is untouched
         try:
             model.train(quiet=True)
+            if test_path is not None:                            # Sparse_Graph_Model.test (:373-385) on a held-out file / fold
+                state.update(epoch=99, fold=None, step=0)
+                model.test(RichPath.create(test_path), quiet=True)
         finally:
             import time as real_time
             sgm.time = real_time
@@ -119,7 +127,7 @@ class ScriptedModel:
     """The scaffold interface training.run_epoch drives, answering with the scripted metrics."""
 
     def __init__(self, task, task_ids):
-        self.task, self.task_ids, self.epoch, self.fold, self.step, self.calls = task, task_ids, 1, None, 0, []
+        self.task, self.task_ids, self.epoch, self.fold, self.step, self.calls, self.testing = task, task_ids, 1, None, 0, [], False
 
     def _next(self, fold, num_graphs):
         if fold != self.fold:
@@ -143,12 +151,14 @@ class ScriptedModel:
         return tb
 
     def task_metrics(self, tb, targets):
-        self.calls.append({"fold": "valid", "epoch": self.epoch, "num_graphs": tb.batch.num_graphs, "num_nodes": tb.batch.num_nodes,
-                           "first_feature_row": tb.batch.node_features[0]})
-        return self._next("valid", tb.batch.num_graphs)
+        fold = "test" if self.testing else "valid"
+        self.calls.append({"fold": fold, "epoch": 99 if self.testing else self.epoch, "num_graphs": tb.batch.num_graphs,
+                           "num_nodes": tb.batch.num_nodes, "first_feature_row": tb.batch.node_features[0]})
+        return self._next(fold, tb.batch.num_graphs)
 
 
-def run_package_loop(task, train_samples, valid_samples, task_ids, best_model_file, max_nodes=MAX_NODES):
+def run_package_loop(task, train_samples, valid_samples, task_ids, best_model_file, max_nodes=MAX_NODES, test_samples=None,
+                     test_description=""):
     def batches(samples, shuffle):
         def make():
             if shuffle:
@@ -162,6 +172,10 @@ def run_package_loop(task, train_samples, valid_samples, task_ids, best_model_fi
                          to_device=lambda tb: (tb, None, None, None), max_epochs=10000, patience=PATIENCE, log=lines.append,
                          save_best=lambda: saves.append(model.epoch), best_model_file=best_model_file, task_ids=task_ids,
                          clock=make_counter_clock())
+    if test_samples is not None:
+        model.testing = True
+        training.test(model, task, batches(test_samples, False)(), to_device=lambda tb: (tb, None, None, None),
+                      data_description=test_description, log=lines.append, task_ids=task_ids, clock=make_counter_clock())
     return lines, model.calls, saves, res
 
 
@@ -173,34 +187,47 @@ def compare(ref_lines, ref_calls, pkg_lines, pkg_calls):
         assert (a["fold"], a["epoch"], a["num_graphs"], a["num_nodes"]) == (b["fold"], b["epoch"], b["num_graphs"], b["num_nodes"])
         assert np.array_equal(a["first_feature_row"], np.asarray(b["first_feature_row"], np.float32))
         assert a["keep_prob_fed"] == (a["fold"] == "train")       # dropout keep-prob only fed while training (:277-279)
+    assert {c["fold"] for c in ref_calls} == {"train", "valid", "test"}
 
 
 def test_qm9_epoch_loop_writes_the_references_log(tmp_path):
     train_recs, valid_recs = write_qm9_folds(str(tmp_path))
     task_ids = [0, 4]
+    test_file = os.path.join(str(tmp_path), "heldout.jsonl.gz")
+    with gzip.open(test_file, "wt") as f:
+        for r in (train_recs + valid_recs)[40:120]:
+            f.write(json.dumps(r) + "\n")
     ref_lines, ref_calls, best_file, saved = run_reference_loop(
         "qm9", str(tmp_path), {"task_ids": task_ids},
-        {"hidden_size": 16, "graph_num_layers": 1, "max_nodes_in_batch": MAX_NODES, "patience": PATIENCE, "random_seed": SEED})
+        {"hidden_size": 16, "graph_num_layers": 1, "max_nodes_in_batch": MAX_NODES, "patience": PATIENCE, "random_seed": SEED},
+        test_path=test_file)
     assert saved
     L = batching.qm9_num_edge_types(train_recs + valid_recs)
     samples = lambda recs: [batching.qm9_graph_to_sample(r, L) for r in recs]
-    pkg_lines, pkg_calls, saves, res = run_package_loop("qm9", samples(train_recs), samples(valid_recs), task_ids, best_file)
+    held_out = samples(batching.load_qm9_jsonl(test_file))
+    pkg_lines, pkg_calls, saves, res = run_package_loop("qm9", samples(train_recs), samples(valid_recs), task_ids, best_file,
+                                                        test_samples=held_out, test_description=test_file)
     compare(ref_lines, ref_calls, pkg_lines, pkg_calls)
     assert saves == [1, 2, 3] and res["best_epoch"] == 3
-    assert pkg_lines[-2] == "Stopping training after %d epochs without improvement on validation loss." % PATIENCE
-    assert pkg_lines[-1].startswith("Training took ") and "MAEs: 0:" in pkg_lines[-1] and "Error Ratios: 0:" in pkg_lines[-1]
+    assert pkg_lines[-5] == "Stopping training after %d epochs without improvement on validation loss." % PATIENCE
+    assert pkg_lines[-4].startswith("Training took ") and "MAEs: 0:" in pkg_lines[-4] and "Error Ratios: 0:" in pkg_lines[-4]
+    assert pkg_lines[-3] == "== Running Test on %s ==" % test_file and pkg_lines[-2].startswith("Loss 0.5") and pkg_lines[-2].endswith(" on 80 graphs")
+    assert pkg_lines[-1].startswith("Metrics: MAEs: 0:")
 
 
 def test_ppi_epoch_loop_writes_the_references_log(tmp_path):
     d = str(tmp_path)
     BC.write_ppi_dir(d, "train", seed=1, num_graphs=9)
     BC.write_ppi_dir(d, "valid", seed=2, num_graphs=4)
+    BC.write_ppi_dir(d, "test", seed=3, num_graphs=3)
     ref_lines, ref_calls, best_file, saved = run_reference_loop(
         "ppi", d, {}, {"hidden_size": 16, "graph_num_layers": 1, "max_nodes_in_batch": 120, "patience": PATIENCE, "random_seed": SEED},
-        max_nodes=120)
+        max_nodes=120, test_path=d)
     assert saved
     tr, _ = batching.load_ppi_fold(d, "train")
     va, _ = batching.load_ppi_fold(d, "valid")
-    pkg_lines, pkg_calls, saves, res = run_package_loop("ppi", list(tr), list(va), (0,), best_file, max_nodes=120)
+    te, _ = batching.load_ppi_fold(d, "test")
+    pkg_lines, pkg_calls, saves, res = run_package_loop("ppi", list(tr), list(va), (0,), best_file, max_nodes=120,
+                                                        test_samples=list(te), test_description=d)
     compare(ref_lines, ref_calls, pkg_lines, pkg_calls)
-    assert saves == [1, 2, 3] and "Avg MicroF1: " in pkg_lines[-1]
+    assert saves == [1, 2, 3] and pkg_lines[-1].startswith("Metrics: Avg MicroF1: ") and pkg_lines[-3] == "== Running Test on %s ==" % d

@@ -148,3 +148,16 @@ def train(model, optimizer, task: str, train_batches: Callable[[], Iterable[Task
             log("Training took %is. Best validation results: %s" % (clock() - total_start, best_descr))
             break
     return {"best_valid_metric": best_metric, "best_epoch": best_epoch, "best_description": best_descr, "history": history}
+
+
+def test(model, task: str, batches: Iterable[TaskBatch], to_device: Callable[[TaskBatch], Tuple], data_description: str = "",
+         log: Callable[[str], None] = print, task_ids: Sequence[int] = (0,), clock: Callable[[], float] = time.time) -> Dict[str, Any]:
+    """Sparse_Graph_Model.test (models/sparse_graph_model.py:373-385): one evaluation epoch over ``batches`` and the three log
+    lines of the reference.  (test.py:27 doubles max_nodes_in_batch for it -- the caller's choice when building ``batches``.)"""
+    log("== Running Test on %s ==" % (data_description,))
+    loss, metrics, num_graphs, _, _, _ = run_epoch(model, None, batches, False, to_device, "Test", clock=clock)
+    log("Loss %.5f on %i graphs" % (loss, num_graphs))
+    descr = pretty_print_epoch_task_metrics(task, metrics, num_graphs, task_ids)
+    log("Metrics: %s" % descr)
+    return {"loss": loss, "num_graphs": num_graphs, "description": descr, "task_metric_results": metrics}
+
