@@ -1,7 +1,7 @@
 // gemm_tcgen05.cu -- C = epilogue([A1|A2] . [B1;B2]) on the 5th-gen tensor cores (tcgen05, sm_100a).
 //
-// Same contract as gemm_tf32x3.cu (fp32 in / fp32 out, fp32-level accuracy through 3xTF32 split
-// accumulation), but on the Blackwell-native path: the legacy mma.sync TF32 pipe tops out at
+// Contract: fp32 in / fp32 out, fp32-level accuracy through 3xTF32 split accumulation (as round 1's mma.sync
+// kernel gemm_tf32x3.cu, removed in round 2), on the Blackwell-native path: the legacy mma.sync TF32 pipe tops out at
 // ~240 TFLOP/s on B200 (profiles/r01_gemm_mma_sync.txt), i.e. 3xTF32 there is no faster than FFMA.
 //
 //   * accumulator: 128 x BN fp32 tile in TMEM (tcgen05.alloc), BN in {32..256} chosen per problem so the
