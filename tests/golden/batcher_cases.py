@@ -129,7 +129,7 @@ def repo_feed(batch, extra):
 
 def repo_qm9_feeds(params, max_nodes, path=QM9_SUBSET):
     import importlib
-    batching = importlib.import_module("tf-gnn-samples_b200.batching")
+    batching = importlib.import_module("tf_gnn_samples_b200.batching")
     self_loops, tied = params.get("add_self_loop_edges", True), params.get("tie_fwd_bkwd_edges", True)
     task_ids = params.get("task_ids", [0])
     recs = batching.load_qm9_jsonl(path)
@@ -145,7 +145,7 @@ def repo_qm9_feeds(params, max_nodes, path=QM9_SUBSET):
 
 def repo_ppi_feeds(params, max_nodes, data_dir):
     import importlib
-    batching = importlib.import_module("tf-gnn-samples_b200.batching")
+    batching = importlib.import_module("tf_gnn_samples_b200.batching")
     graphs, labels = batching.load_ppi_fold(data_dir, "test", params.get("add_self_loop_edges", True),
                                             params.get("tie_fwd_bkwd_edges", False))
     feeds = []

@@ -108,8 +108,8 @@ def adjacency_of(feed, num_edge_types):
 
 def run_oracle(case, feed, variables, params, task_params, num_edge_types, dtype=np.float64):
     from oracle import ref_model
-    ck = importlib.import_module("tf-gnn-samples_b200.checkpoint")
-    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    ck = importlib.import_module("tf_gnn_samples_b200.checkpoint")
+    scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
     srt = ck.sort_variables(variables)
     assert not srt["unused"], srt["unused"]
     kind = case["kind"]

@@ -22,7 +22,7 @@ for p in (HERE, os.path.join(HERE, "golden")):
 
 import batcher_cases as BC      # noqa: E402
 
-batching = importlib.import_module("tf-gnn-samples_b200.batching")
+batching = importlib.import_module("tf_gnn_samples_b200.batching")
 FIXTURE = os.path.join(HERE, "golden", "ref_batcher_feeds.npz")
 have_reference = pytest.mark.skipif(not os.path.isdir("/root/reference/tasks"), reason="the reference checkout is not on this box")
 

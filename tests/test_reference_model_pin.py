@@ -28,7 +28,7 @@ for p in (HERE, os.path.join(HERE, "golden")):
 import batcher_cases as BC      # noqa: E402
 import model_cases as MC        # noqa: E402
 
-checkpoint = importlib.import_module("tf-gnn-samples_b200.checkpoint")
+checkpoint = importlib.import_module("tf_gnn_samples_b200.checkpoint")
 have_reference = pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference checkout is not on this box")
 ALL = sorted(MC.CASES)
 
@@ -84,7 +84,7 @@ def test_snapshot_loads_into_the_scaffold_by_variable_name(name, ppi_dir):
     """Every parameter of SparseGraphModel receives the value the oracle reads for it (same sorted dictionaries), none is left
     at its initial value, and the parameter count is the one the reference printed."""
     import torch
-    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
     case = MC.CASES[name]
     z, snap = fixture(name)
     feed, L = repo_feed(case, snap.task_params, ppi_dir)
@@ -125,7 +125,7 @@ def test_snapshot_loads_into_the_scaffold_by_variable_name(name, ppi_dir):
 def test_default_params_of_the_snapshots_are_the_packages():
     """model_params in the reference's pickle = <X>_Model.default_params() + the case's overrides; scaffold.model_default_params
     restates those defaults (keys the loops never read -- max_epochs, patience, lr_for_num_graphs_per_batch -- aside)."""
-    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
     for name in ALL:
         case = MC.CASES[name]
         _, snap = fixture(name)
@@ -159,7 +159,7 @@ def test_fixture_equals_the_reference_scaffold_run_here(name):
 def test_readme_parameter_count_by_the_references_own_loop():
     """README.md:29 'Model has 699257 parameters' (RGCN on PPI: 50 features, 121 labels, 3 edge types, hidden 256, 3 layers),
     counted by sparse_graph_model.py:153-157 over the variables the reference's scaffold creates -- and by the package."""
-    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
     case = dict(kind="rgcn", task="ppi", model_params={"hidden_size": 256, "graph_num_layers": 3}, task_params={}, budget=10 ** 6)
     r = MC.run_reference(case, np.float32, ppi_kw=dict(feature_dim=50, num_labels=121))
     assert r["num_parameters"] == 699257
@@ -170,7 +170,7 @@ def test_readme_parameter_count_by_the_references_own_loop():
 @have_reference
 def test_default_params_equal_the_reference_classes():
     import tf1_shim
-    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
     with tf1_shim.installed():
         tf1_shim.import_reference_task("sparse_graph_task")
         import models
@@ -188,7 +188,7 @@ EXPORT_CASES = ["rgcn_ppi_scaffold", "film_ppi_scaffold", "rgin_ppi_scaffold", "
 
 
 def _package_model(case, feed, L, seed):
-    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+    scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
     params = dict(scaffold.model_default_params(case["kind"]), **case["model_params"], random_seed=seed)
     task_params = dict({"task_ids": [0]} if case["task"] == "qm9" else {}, **case["task_params"])
     kw = dict(num_labels=feed["target_labels"].shape[1]) if case["task"] == "ppi" else dict(task_ids=tuple(task_params["task_ids"]))
@@ -284,8 +284,8 @@ def test_train_step_construction_and_per_tensor_clipping(optimizer, ppi_dir):
     that the differentiated quantity is task_metrics['loss'], and that every gradient is clipped BY ITS OWN norm (tf.clip_by_norm,
     not a global norm), None gradients passing through -- against scaffold.make_optimizer / clip_gradients_ on the same numbers."""
     import torch
-    scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
-    tfo = importlib.import_module("tf-gnn-samples_b200.tf_optimizers")
+    scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
+    tfo = importlib.import_module("tf_gnn_samples_b200.tf_optimizers")
     hp = {"optimizer": optimizer, "learning_rate": 0.003, "learning_rate_decay": 0.9, "momentum": 0.7, "clamp_gradient_norm": 0.5}
     case = dict(MC.CASES["film_ppi_scaffold"], model_params=dict(MC.CASES["film_ppi_scaffold"]["model_params"], **hp))
     rng = np.random.default_rng(8)
@@ -316,7 +316,7 @@ def test_train_step_construction_and_per_tensor_clipping(optimizer, ppi_dir):
         assert cls_name == "AdamOptimizer" and kwargs == {"learning_rate": 0.003}
         assert isinstance(opt, tfo.TF1Adam) and opt.defaults["lr"] == 0.003 and opt.defaults["epsilon"] == 1e-8
     # the package's clipping on the same gradients, parameters matched to variables by the exported names
-    checkpoint_mod = importlib.import_module("tf-gnn-samples_b200.checkpoint")
+    checkpoint_mod = importlib.import_module("tf_gnn_samples_b200.checkpoint")
     named = checkpoint_mod.model_to_variables(model.projection, model.layers, "ppi", model.head)
     assert set(named) == set(prescribed)
     for name, p in named.items():

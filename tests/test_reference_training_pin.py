@@ -25,8 +25,8 @@ for p in (HERE, os.path.join(HERE, "golden")):
 import batcher_cases as BC      # noqa: E402
 
 pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference checkout is not on this box")
-batching = importlib.import_module("tf-gnn-samples_b200.batching")
-training = importlib.import_module("tf-gnn-samples_b200.training")
+batching = importlib.import_module("tf_gnn_samples_b200.batching")
+training = importlib.import_module("tf_gnn_samples_b200.training")
 
 PATIENCE, MAX_NODES, SEED = 2, 700, 4
 

@@ -14,8 +14,8 @@ if HERE not in sys.path:
     sys.path.insert(0, HERE)
 
 pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/utils"), reason="the reference checkout is not on this box")
-mine = importlib.import_module("tf-gnn-samples_b200.utils")
-scaffold = importlib.import_module("tf-gnn-samples_b200.scaffold")
+mine = importlib.import_module("tf_gnn_samples_b200.utils")
+scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
 
 ACTIVATION_NAMES = [None, "linear", "Linear", "tanh", "TANH", "relu", "ReLU", "leaky_relu", "Leaky_ReLU", "elu", "ELU", "selu", "gelu",
                     "GeLU", "sigmoid", "swish", "", "relu ", "leaky-relu"]
@@ -114,7 +114,7 @@ def test_layer_function_signatures_equal_the_references(reference):
     the same order with the same defaults, plus keyword-only extras (weights=, plan=, ...) that the reference cannot know."""
     import inspect
     import gnns as ref_gnns                                   # the reference's package (inside the fixture's installed() block)
-    pkg = importlib.import_module("tf-gnn-samples_b200.gnns")
+    pkg = importlib.import_module("tf_gnn_samples_b200.gnns")
     names = [n for n in dir(ref_gnns) if n.startswith("sparse_") and n.endswith("_layer")]
     assert sorted(names) == ["sparse_ggnn_layer", "sparse_gnn_edge_mlp_layer", "sparse_gnn_film_layer", "sparse_rgat_layer",
                              "sparse_rgcn_layer", "sparse_rgdcn_layer", "sparse_rgin_layer"]
