@@ -332,3 +332,28 @@ def test_train_step_construction_and_per_tensor_clipping(optimizer, ppi_dir):
         else:
             assert np.allclose(p.grad.numpy(), applied[name], rtol=2e-6, atol=1e-9), name
             assert float(np.linalg.norm(applied[name])) <= 0.5 * (1 + 1e-12)
+
+
+@have_reference
+def test_learning_rate_normalised_per_graph_count(ppi_dir):
+    """lr_for_num_graphs_per_batch = n (sparse_graph_model.py:230-238): the reference hands the optimizer
+    learning_rate * num_graphs / n; set_learning_rate_ puts the same number into the torch optimizer before the step."""
+    scaffold = importlib.import_module("tf_gnn_samples_b200.scaffold")
+    hp = {"optimizer": "RMSProp", "learning_rate": 0.003, "lr_for_num_graphs_per_batch": 30}
+    case = dict(MC.CASES["rgcn_qm9"], model_params=dict(MC.CASES["rgcn_qm9"]["model_params"], **hp))
+    r = MC.run_reference(case, np.float32)
+    (cls_name, kwargs), = r["optimizers"]
+    G = int(r["feed"]["num_graphs"])
+    assert cls_name == "RMSPropOptimizer" and G not in (0, 30)
+    model = scaffold.SparseGraphModel("rgcn", "qm9", r["num_edge_types"], 15, params=r["params"], task_ids=(0, 4), device="cpu")
+    opt = model.make_optimizer()
+    assert opt.param_groups[0]["lr"] == 0.003
+    model.set_learning_rate_(opt, G)
+    assert abs(opt.param_groups[0]["lr"] - float(kwargs["learning_rate"])) <= 1e-6 * float(kwargs["learning_rate"])
+    assert abs(opt.param_groups[0]["lr"] - 0.003 * G / 30) <= 1e-9
+    with pytest.raises(ValueError):
+        model.set_learning_rate_(opt, None)
+    plain = scaffold.SparseGraphModel("rgcn", "qm9", 5, 15, params={"hidden_size": 16, "graph_num_layers": 1}, device="cpu")
+    o2 = plain.make_optimizer()
+    plain.set_learning_rate_(o2, None)                           # not configured: untouched, num_graphs not needed
+    assert o2.param_groups[0]["lr"] == plain.params["learning_rate"]

@@ -266,7 +266,7 @@ _BASE_DEFAULTS = {                                             # Sparse_Graph_Mo
     "graph_layer_input_dropout_keep_prob": 0.8, "graph_dense_between_every_num_gnn_layers": 1,
     "graph_model_activation_function": "tanh", "graph_residual_connection_every_num_layers": 2,
     "graph_inter_layer_norm": False, "optimizer": "Adam", "learning_rate": 0.001, "learning_rate_decay": 0.98,
-    "momentum": 0.85, "clamp_gradient_norm": 1.0, "random_seed": 0,
+    "momentum": 0.85, "clamp_gradient_norm": 1.0, "random_seed": 0, "lr_for_num_graphs_per_batch": None,
 }
 _MODEL_DEFAULTS = {                                            # <X>_Model.default_params overlays (models/*_model.py)
     "rgcn": {"hidden_size": 128, "graph_activation_function": "ReLU", "message_aggregation_function": "sum",
@@ -474,12 +474,26 @@ class SparseGraphModel(torch.nn.Module):
     make_optimizer = RGCNPPIModel.make_optimizer
     clip_gradients_ = RGCNPPIModel.clip_gradients_
 
+    def set_learning_rate_(self, optimizer, num_graphs: Optional[int]) -> None:
+        """models/sparse_graph_model.py:230-238: with ``lr_for_num_graphs_per_batch`` = n the step's learning rate is
+        learning_rate * num_graphs / n (evaluated in float32 there), so the rate PER GRAPH stays fixed while the packed batches
+        vary in size.  Only the VarMisuse hyper-parameter files set it; None (the default) leaves the optimizer alone."""
+        n = self.params.get("lr_for_num_graphs_per_batch")
+        if n is None:
+            return
+        if num_graphs is None:
+            raise ValueError("lr_for_num_graphs_per_batch is set: train_step needs num_graphs")
+        lr = float(self.params["learning_rate"]) * float(np.float32(num_graphs) / np.float32(n))
+        for group in optimizer.param_groups:
+            group["lr"] = lr
+
     def train_step_async(self, optimizer, features, plan, num_incoming, targets, graph_nodes_list=None,
                          num_graphs: Optional[int] = None, group=None, global_count_: Optional[float] = None) -> Dict[str, torch.Tensor]:
         """``global_count_``: nodes (PPI) / graphs (QM9) of the union batch over all ranks -> data-parallel step
         (see RGCNPPIModel.train_step_async)."""
         self.train()
         optimizer.zero_grad(set_to_none=True)
+        self.set_learning_rate_(optimizer, num_graphs)
         m = self.task_metrics(self(features, plan, num_incoming, graph_nodes_list, num_graphs), targets)
         if global_count_ is None:
             m["loss"].backward()
