@@ -120,3 +120,24 @@ def test_minibatches_refuse_a_graph_that_can_never_fit():
     n = graphs[1].node_features.shape[0]
     with pytest.raises(ValueError, match="does not fit"):
         list(batching.minibatches(graphs, n))       # node_offset + n < n is false even for an empty batch
+
+
+@have_reference
+def test_the_full_qm9_validation_set_is_packed_like_the_reference():
+    """BASELINE config 3's batch: all 10,000 validation molecules of data/qm9/valid.jsonl.gz through the reference's loader and
+    batcher in ONE minibatch (V = 180,560, M = 554,026, L = 5) against batching.py -- every edge in the same position."""
+    path = "/root/reference/data/qm9/valid.jsonl.gz"
+    if not os.path.exists(path):
+        pytest.skip("reference data not present")
+    want, L = BC.reference_qm9_feeds({}, 10 ** 9, path=path)
+    got, L2 = BC.repo_qm9_feeds({}, 10 ** 9, path=path)
+    assert L == L2 == 5 and len(want) == 1
+    assert (int(want[0]["num_graphs"]), int(want[0]["num_nodes"]), int(want[0]["num_edges"])) == (10000, 180560, 554026)
+    BC.compare_feeds(got, want, "qm9 valid.jsonl.gz")
+    # the structure-only archive the GPU box uses for config 3 (bench.py, test_reference_pin.py) rebuilds the same graph
+    recs = batching.qm9_records_from_structure(os.path.join(HERE, "golden", "qm9_valid_structure.npz"))
+    b, graph_nodes_list, _ = batching.qm9_batch(recs)
+    assert np.array_equal(graph_nodes_list, want[0]["graph_nodes_list"])
+    assert np.array_equal(b.type_to_num_incoming_edges, np.asarray(want[0]["type_to_num_incoming_edges"], np.float32))
+    for i, a in enumerate(b.adjacency_lists):
+        assert np.array_equal(a, want[0]["adjacency_e%d" % i]), "edge type %d" % i
