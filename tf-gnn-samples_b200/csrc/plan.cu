@@ -377,7 +377,7 @@ extern "C" int rgnn_plan_create_ex(rgnn_plan_t** out, int32_t num_nodes, int32_t
     size_t scan_bytes = 0;
     PLAN_CUDA2(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(VL + 1), stream));
     scan_bytes = align_up(scan_bytes, 256);
-    PLAN_CUDA2(cudaMallocAsync(&plan->pair_block, 2 * m_bytes + 256, stream));
+    PLAN_CUDA2(cudaMallocAsync(&plan->pair_block, 2 * m_bytes + align_up(sizeof(int32_t) * (RGNN_MAX_EDGE_TYPES + 1), 256), stream));
     char* pb = static_cast<char*>(plan->pair_block);
     plan->pair_src = reinterpret_cast<int32_t*>(pb);
     plan->e_pair = reinterpret_cast<int32_t*>(pb + m_bytes);
