@@ -118,3 +118,37 @@ def test_prefetch_keeps_order_bounds_the_queue_and_propagates_errors():
             got.append(v)
     assert got == [0, 1, 2]
     assert list(training.prefetch([], fn)) == []
+
+
+def test_train_step_async_plumbing_on_the_host():
+    """SparseGraphModel.train_step_async with the GNN forward replaced by a host computation: learning-rate normalisation,
+    backward of task_metrics['loss'], per-tensor clipping and the optimizer step run in the order of __make_train_step."""
+    import torch
+    from tf_gnn_samples_b200.scaffold import SparseGraphModel
+
+    class HostModel(SparseGraphModel):
+        def forward(self, features, plan, num_incoming, graph_nodes_list=None, num_graphs=None):
+            final = torch.tanh(features @ self.projection)
+            outs = []
+            for hd in self.head:
+                gate = torch.sigmoid(torch.cat([final, features], dim=-1) @ hd["gate_kernel"] + hd["gate_bias"])
+                per_node = gate * (final @ hd["kernel"] + hd["bias"])
+                outs.append(torch.zeros(num_graphs, 1).index_add_(0, graph_nodes_list, per_node)[:, 0])
+            return torch.stack(outs)
+
+    torch.manual_seed(0)
+    params = {"hidden_size": 8, "graph_num_layers": 1, "optimizer": "RMSProp", "learning_rate": 0.01, "lr_for_num_graphs_per_batch": 4,
+              "clamp_gradient_norm": 0.05}
+    m = HostModel("rgcn", "qm9", 2, 5, params=params, task_ids=(0,), device="cpu")
+    opt = m.make_optimizer()
+    feats, ids = torch.randn(9, 5), torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2])
+    targets = torch.randn(1, 3)
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    out = m.train_step_async(opt, feats, None, None, targets, ids, 3)
+    assert opt.param_groups[0]["lr"] == pytest.approx(0.01 * 3 / 4)                  # 3 graphs in the batch, normalised to 4
+    assert set(out) >= {"loss", "total_loss", "abs_err_task0"} and float(out["total_loss"]) == pytest.approx(3 * float(out["loss"]))
+    used = [n for n, p in m.named_parameters() if p.grad is not None]
+    assert "projection" in used and all(float(m.get_parameter(n).grad.norm()) <= 0.05 * (1 + 1e-5) for n in used)
+    assert any(not torch.equal(p.detach(), before[n]) for n, p in m.named_parameters())
+    with pytest.raises(ValueError):
+        m.train_step_async(opt, feats, None, None, targets, ids, None)               # the normalisation needs the graph count
