@@ -1,5 +1,6 @@
 """torch-CPU float32 restatement of the reference layers in the reference's op order
-(TEST / BASELINE INFRASTRUCTURE -- see oracle/__init__.py; PARITY UNPINNED).
+(TEST / BASELINE INFRASTRUCTURE -- see oracle/__init__.py).  PINNED: tests/test_cpu_baseline_pin.py compares it with the
+output of the reference's own gnns/rgcn.py at BASELINE config 2 (tests/golden/ref_config2_rgcn_ppi.npz) and with the numpy oracle.
 
 This is the timed stand-in for "the reference TF1 CPU path" (BASELINE.md 3): per edge type
 index_select (tf.nn.embedding_lookup, gnns/rgcn.py:88) -> [E_l, D] @ [D, D] (Dense, :98) ->
