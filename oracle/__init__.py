@@ -20,5 +20,7 @@ Modules:
   ref_layers  numpy restatement (dtype-parametric: float64 "truth", float32
               "reference order") of the six sparse_*_layer functions.
   ref_torch   torch-CPU float32 restatement in reference op order (the timed
-              stand-in for "the reference TF1 CPU path").
+              stand-in for "the reference TF1 CPU path"; pinned by tests/test_cpu_baseline_pin.py).
+  ref_model   whole-model forward + task heads (pinned against the reference's own scaffold:
+              tests/test_reference_model_pin.py).
 """

@@ -1,9 +1,10 @@
 """Differentiable restatement of the reference layers in torch float64 on the CPU (TEST INFRASTRUCTURE -- see
 oracle/__init__.py; never imported by the product).
 
-PARITY UNPINNED (the reference has no tests or golden vectors and TF1 cannot run here).  This file is pinned
-instead against oracle/ref_layers.py (the numpy restatement) in tests/test_oracle_autograd.py, and its gradients
-by torch.autograd.gradcheck there.
+Pinning: the FORWARD of every function here equals oracle/ref_layers.py (tests/test_oracle_autograd.py), which is held at 1e-12
+to the reference's own executed code (tests/test_reference_pin.py, tests/test_reference_fuzz.py); the GRADIENTS are then the
+derivatives of a pinned function, checked by torch.autograd.gradcheck.  (TF's autodiff itself cannot run here -- there is no
+reference-produced gradient to compare with.)
 
 Purpose: the reference gets its gradients from TF autodiff of exactly these op graphs
 (models/sparse_graph_model.py:253-260), so torch autograd over the same op order in float64 is the gradient truth

@@ -1,4 +1,5 @@
-"""Analytic gradients of the RGCN layer in numpy (TEST INFRASTRUCTURE -- see oracle/__init__.py; PARITY UNPINNED).
+"""Analytic gradients of the RGCN layer in numpy (TEST INFRASTRUCTURE -- see oracle/__init__.py; derivatives of the PINNED
+forward oracle.ref_layers.sparse_rgcn_layer, checked by finite differences -- TF autodiff itself cannot run here).
 
 The reference gets its gradients from TensorFlow autodiff of gnns/rgcn.py:84-114
 (models/sparse_graph_model.py:253-260 calls tf.gradients on the loss).  This restates what autodiff

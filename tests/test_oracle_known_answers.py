@@ -1,6 +1,7 @@
 """CPU: pin the oracle with everything the reference offers -- the structural
 parameter count of README.md:29 -- plus hand-computable graphs and algebraic identities.  The reference has
-no golden vectors (parity unpinned), so these are the known-answer tests the oracle itself must pass."""
+no golden vectors of its own; since round 2 the oracle is ALSO held to the reference's executed code
+(test_reference_pin.py, test_reference_fuzz.py) -- these known-answer tests stay as the independent check."""
 import numpy as np
 import pytest
 
